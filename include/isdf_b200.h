@@ -1,0 +1,160 @@
+/*
+ * isdf_b200 -- C ABI of the B200 (sm_100a) implementation of the iSDF training hot path.
+ *
+ * The reference (facebookresearch/iSDF) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md 8b); every entry point below replaces a block of reference Python that the
+ * host-side mirror in isdf_b200/modules/ calls through ctypes.  The reference interface
+ * each one stands in for is cited as  <file>:<lines>  relative to /root/reference/.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative isdfb_status otherwise; the message is
+ *     available from isdfb_last_error(ctx) (or isdfb_last_error(NULL) for create failures);
+ *   - all data pointers are caller-owned DEVICE pointers (torch storage) unless the name
+ *     says `host`; fp32 unless stated; indices are int64 as in the reference;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the device, nothing
+ *     allocates after isdfb_create (workspaces are sized by max_points);
+ *   - calls may come from any host thread (train_vis.py steps from a worker thread):
+ *     every call does cudaSetDevice(ctx->device) itself.
+ */
+#ifndef ISDF_B200_H_
+#define ISDF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct isdfb_ctx isdfb_ctx;
+
+typedef enum {
+  ISDFB_OK = 0,
+  ISDFB_ERR_ARG = -1,        /* bad argument / unsupported configuration */
+  ISDFB_ERR_CUDA = -2,       /* CUDA runtime error (message carries cudaGetErrorString) */
+  ISDFB_ERR_CAPACITY = -3,   /* batch larger than the workspace / TMEM / smem budget */
+  ISDFB_ERR_STATE = -4       /* call order violated (e.g. weights not packed) */
+} isdfb_status;
+
+typedef enum {
+  ISDFB_PREC_FP32 = 0,       /* fp32 CUDA-core path (exact-parity mode, also the on-device check) */
+  ISDFB_PREC_BF16X3 = 1,     /* tcgen05 kind::f16, bf16 hi/lo split, 3 MMAs per product (~fp32) */
+  ISDFB_PREC_BF16 = 2        /* tcgen05 kind::f16, single bf16 pass (fast mode) */
+} isdfb_precision;
+
+/* Model description: fc_map.py:63-111 (SDFMap.__init__), embedding.py:25-66. */
+typedef struct {
+  int32_t n_freqs;           /* max_deg - min_deg + 1 (6 at default)            */
+  int32_t hidden;            /* hidden_feature_size (256)                       */
+  int32_t block;             /* hidden_layers_block (2)                         */
+  int32_t has_transform;     /* 1 if `transform` below is used (embedding.py:12-22) */
+  float scale_input;         /* PostionalEncoding.scale                         */
+  float scale_output;        /* SDFMap.scale_output                             */
+  float transform[12];       /* rows of the 3x4 [R|t] of PostionalEncoding.transform */
+  int32_t precision;         /* isdfb_precision                                 */
+  int32_t max_points;        /* workspace capacity in points per internal chunk */
+} isdfb_model_cfg;
+
+/* Loss hyper-parameters: trainer.py:303-318, loss.py:122-205. */
+typedef struct {
+  float trunc_weight, trunc_distance;
+  float eik_weight, eik_apply_dist;
+  float grad_weight;
+  int32_t orien_loss;        /* loss.orien_loss                                  */
+  int32_t loss_type;         /* 1 = L1, 2 = L2                                   */
+  float noise_std;           /* SDFMap.forward noise_std (0 = none)              */
+  float inv_count;           /* 1 / (number of valid samples the mean runs over) */
+} isdfb_loss_cfg;
+
+/* Camera intrinsics: transform.py:13-33 (ray_dirs_C, depth_type 'z'). */
+typedef struct { float fx, fy, cx, cy; int32_t H, W; } isdfb_camera;
+
+/* ---- lifetime ----------------------------------------------------------------------- */
+int isdfb_create(const isdfb_model_cfg* cfg, int device, isdfb_ctx** out);
+int isdfb_destroy(isdfb_ctx* ctx);
+const char* isdfb_last_error(const isdfb_ctx* ctx);
+/* number of fp32 parameters in SDFMap.parameters() order (fc_map.py:77-90) */
+int64_t isdfb_param_count(const isdfb_ctx* ctx);
+int32_t isdfb_embedding_size(const isdfb_ctx* ctx);
+/* how many of this library's kernels have been launched on this ctx since creation */
+int64_t isdfb_launch_count(const isdfb_ctx* ctx);
+
+/* ---- weights ------------------------------------------------------------------------
+ * Re-packs the flat fp32 parameters (SDFMap.parameters() order, PyTorch [out,in] layout)
+ * into the padded / tensor-core operand images the kernels consume.  Replaces nothing in
+ * the reference (cuBLAS reads nn.Linear weights directly, fc_map.py:99-104); it is the
+ * price of the MMA operand layout and is folded into isdfb_adamw on the training path.   */
+int isdfb_pack_weights(isdfb_ctx* ctx, const float* params_flat, void* stream);
+
+/* ---- K1: ray / depth sampling --------------------------------------------------------
+ * isdfb_gather_rays   = sample.get_batch_data without the compaction (sample.py:24-74):
+ *   depth_out[r] = depth[fmap[ib[r]], ih[r], iw[r]]; normal_out likewise (normals indexed by
+ *   ib[r] directly -- reference quirk Q1, trainer.py:956,965-969 -- unless
+ *   normals_use_frame_map != 0); valid[r] = depth!=0 &&
+ *   !isnan(normal.x).  frame_map may be NULL (identity).  normals may be NULL.
+ * isdfb_sample_rays   = transform.origin_dirs_W + sample.stratified_sample +
+ *   sample.sample_along_rays (transform.py:36-41, sample.py:77-178) for already-compacted rays:
+ *   z = [depth, clamp(depth+n_near, min_depth, depth+dist_behind), strat bins]; pc = o + d_W z.
+ *   `lin` is torch.linspace(0,1,n_strat+1) (passed in so bin edges are bit-identical).       */
+int isdfb_gather_rays(isdfb_ctx* ctx, const float* depth, const float* normals,
+                      const int64_t* frame_map, int32_t normals_use_frame_map,
+                      const int64_t* ib, const int64_t* ih, const int64_t* iw, int64_t n_rays,
+                      const isdfb_camera* cam, float* depth_out, float* normal_out,
+                      uint8_t* valid_out, void* stream);
+int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC /*[F,4,4]*/, const int64_t* frame_map,
+                      const int64_t* ib, const int64_t* ih, const int64_t* iw,
+                      const float* depth_sample, const float* u_strat, const float* n_near,
+                      const float* lin, int64_t n_rays, int32_t n_strat, int32_t n_surf,
+                      const isdfb_camera* cam, float min_depth, float dist_behind,
+                      float* pc /*[R,S,3]*/, float* z_vals /*[R,S]*/, float* dirs_C /*[R,3]*/,
+                      float* T_WC_sample /*[R,4,4]*/, void* stream);
+
+/* ---- K2 / K3: PE + MLP forward, and forward + input gradient --------------------------
+ * isdfb_mlp_forward       = SDFMap.forward (fc_map.py:94-111) incl. noise and scale_output.
+ * isdfb_mlp_forward_grad  = SDFMap.forward + fc_map.gradient (fc_map.py:12-22).
+ * noise may be NULL.  n is arbitrary (internally chunked / padded).                        */
+int isdfb_mlp_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std,
+                      int64_t n, float* sdf, void* stream);
+int isdfb_mlp_forward_grad(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std,
+                           int64_t n, float* sdf, float* grad, void* stream);
+
+/* ---- K4: fused training forward/backward ----------------------------------------------
+ * Replaces Trainer.sdf_eval_and_loss + total_loss.backward() (trainer.py:768-868, 981):
+ * S1 forward, S2 input gradient, loss.bounds('ray') / sdf_loss / eikonal / normal terms /
+ * tot_loss (loss.py:13-22,48-53,122-205; trainer.py:814-836), S3+S4 double back-prop.
+ * Outputs: sdf[R,S], grad[R,S,3] (may be NULL), loss_mat[R,S] (total per sample),
+ * loss_sums[4] += {sum sdf_loss, sum grad_loss, sum eik_loss(weighted), sum total}
+ * (caller zeroes), and the parameter gradient accumulated into the ctx-internal gradient
+ * buffer (zeroed by isdfb_zero_grad, exported by isdfb_export_grads, consumed by isdfb_adamw).
+ * ray_valid may be NULL (all valid); invalid rays contribute nothing.                       */
+int isdfb_train_fwd_bwd(isdfb_ctx* ctx, const float* pc, const float* z_vals,
+                        const float* depth_sample, const float* dirs_C, const float* T_WC_sample,
+                        const float* norm_sample, const float* noise, const uint8_t* ray_valid,
+                        int64_t n_rays, int32_t n_samples, const isdfb_loss_cfg* loss,
+                        float* sdf, float* grad, float* loss_mat, float* loss_sums, void* stream);
+int isdfb_zero_grad(isdfb_ctx* ctx, void* stream);
+int isdfb_export_grads(isdfb_ctx* ctx, float* grads_flat, void* stream);
+
+/* ---- K5: per-frame loss histogram ------------------------------------------------------
+ * loss.frame_avg + approx_loss (loss.py:208-240) without the [F,H,W] images: per ray sum of
+ * loss_mat over samples, scattered into factor x factor blocks; duplicate pixels are
+ * last-writer-wins and counted once, as CPU index_put does.
+ * loss_approx[F,factor,factor], frame_avg[F].                                              */
+int isdfb_frame_bins(isdfb_ctx* ctx, const float* loss_mat, const uint8_t* ray_valid,
+                     const int64_t* ib, const int64_t* ih, const int64_t* iw, int64_t n_rays,
+                     int32_t n_samples, int32_t n_frames, int32_t H, int32_t W, int32_t factor,
+                     float* loss_approx, float* frame_avg, void* stream);
+
+/* ---- K6: AdamW + weight re-pack --------------------------------------------------------
+ * torch.optim.AdamW.step for the flat parameter vector (trainer.py:435-439, 982) using the
+ * ctx-internal gradient times grad_scale (e.g. 1/world_size after the all-reduce), then
+ * refreshes the packed weights.  m, v: flat fp32 state; step is 1-based.                    */
+int isdfb_adamw(isdfb_ctx* ctx, float* params_flat, float* m, float* v, int64_t step, float lr,
+                float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                void* stream);
+/* ctx-internal gradient buffer (fp32, padded internal layout) for the NCCL all-reduce.     */
+int isdfb_grad_buffer(isdfb_ctx* ctx, float** ptr, int64_t* n_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISDF_B200_H_ */

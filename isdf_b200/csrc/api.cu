@@ -1,0 +1,246 @@
+// C-ABI entry points (include/isdf_b200.h): argument checks, context lifetime, precision dispatch.
+#include "common.cuh"
+#include <new>
+
+char g_isdfb_create_err[512] = "";
+
+int sample_gather(isdfb_ctx*, const float*, const float*, const int64_t*, int, const int64_t*, const int64_t*,
+                  const int64_t*, int64_t, const isdfb_camera*, float*, float*, uint8_t*, cudaStream_t);
+int sample_along(isdfb_ctx*, const float*, const int64_t*, const int64_t*, const int64_t*, const int64_t*,
+                 const float*, const float*, const float*, const float*, int64_t, int, int,
+                 const isdfb_camera*, float, float, float*, float*, float*, float*, cudaStream_t);
+int sample_frame_bins(isdfb_ctx*, float*, const float*, const uint8_t*, const int64_t*, const int64_t*,
+                      const int64_t*, int64_t, int, int, int, int, int, float*, float*, cudaStream_t);
+int tc_create(isdfb_ctx* ctx);
+void tc_destroy(isdfb_ctx* ctx);
+int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n,
+               float* sdf, float* grad, cudaStream_t st);
+int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample,
+             const float* dirs_C, const float* T_WC_sample, const float* norm_sample, const float* noise,
+             const uint8_t* ray_valid, int64_t n_rays, int32_t S, const isdfb_loss_cfg* loss, float* sdf,
+             float* grad, float* loss_mat, float* loss_sums, cudaStream_t st);
+
+static float* g_scratch_of(isdfb_ctx* ctx);
+
+static int build_layout(const isdfb_model_cfg& cfg, ModelLayout* lay, char* err, size_t errn) {
+  if (cfg.n_freqs < 1 || cfg.n_freqs > 16) { snprintf(err, errn, "n_freqs %d out of range", cfg.n_freqs); return ISDFB_ERR_ARG; }
+  if (cfg.block < 1 || 2 * cfg.block + 2 > ISDFB_MAX_HIDDEN_LAYERS) { snprintf(err, errn, "block %d unsupported", cfg.block); return ISDFB_ERR_ARG; }
+  if (cfg.hidden % 128 != 0 || cfg.hidden <= 0) { snprintf(err, errn, "hidden %d must be a multiple of 128", cfg.hidden); return ISDFB_ERR_ARG; }
+  memset(lay, 0, sizeof(*lay));
+  lay->n_freqs = cfg.n_freqs;
+  lay->E = 2 * ISDFB_NDIRS * cfg.n_freqs + 3;
+  lay->Ep = (int)round_up64(lay->E, 128);
+  lay->H = cfg.hidden;
+  lay->block = cfg.block;
+  lay->L = 2 * cfg.block + 2;
+  const int ic = cfg.block + 1;
+  int64_t po = 0, fo = 0;
+  for (int l = 0; l < lay->L; ++l) {
+    LayerDesc& d = lay->layer[l];
+    d.is_cat = (l == ic);
+    d.k0 = (l == 0) ? lay->Ep : lay->H;
+    d.k0_real = (l == 0) ? lay->E : lay->H;
+    d.flat_in = (l == 0) ? lay->E : (d.is_cat ? lay->H + lay->E : lay->H);
+    d.w_off = po; po += (int64_t)lay->H * d.k0;
+    d.we_off = -1;
+    if (d.is_cat) { d.we_off = po; po += (int64_t)lay->H * lay->Ep; }
+    d.b_off = po; po += lay->H;
+    d.flat_w_off = fo; fo += (int64_t)lay->H * d.flat_in;
+    d.flat_b_off = fo; fo += lay->H;
+  }
+  lay->wout_off = po; po += lay->H;
+  lay->bout_off = po; po += 4;   // keep 16-byte alignment of whatever follows
+  lay->flat_wout_off = fo; fo += lay->H;
+  lay->flat_bout_off = fo; fo += 1;
+  lay->n_packed = po;
+  lay->n_flat = fo;
+  return ISDFB_OK;
+}
+
+extern "C" {
+
+int isdfb_create(const isdfb_model_cfg* cfg, int device, isdfb_ctx** out) {
+  if (!cfg || !out) { snprintf(g_isdfb_create_err, sizeof(g_isdfb_create_err), "null argument"); return ISDFB_ERR_ARG; }
+  isdfb_ctx* ctx = new (std::nothrow) isdfb_ctx();
+  if (!ctx) return ISDFB_ERR_ARG;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  ctx->cfg = *cfg;
+  int rc = build_layout(*cfg, &ctx->lay, g_isdfb_create_err, sizeof(g_isdfb_create_err));
+  if (rc) { delete ctx; return rc; }
+  if (cfg->precision < ISDFB_PREC_FP32 || cfg->precision > ISDFB_PREC_BF16) {
+    snprintf(g_isdfb_create_err, sizeof(g_isdfb_create_err), "unknown precision %d", cfg->precision);
+    delete ctx; return ISDFB_ERR_ARG;
+  }
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) ctx->pe.R[r * 3 + c] = cfg->has_transform ? cfg->transform[r * 4 + c] : (r == c ? 1.f : 0.f);
+    ctx->pe.t[r] = cfg->has_transform ? cfg->transform[r * 4 + 3] : 0.f;
+  }
+  ctx->pe.scale = cfg->scale_input;
+  ctx->pe.n_freqs = cfg->n_freqs;
+  ctx->pe.has_transform = cfg->has_transform;
+  int64_t cap = cfg->max_points > 0 ? cfg->max_points : 32768;
+  ctx->cap = round_up64(cap, ISDFB_TILE);
+
+#define CREATE_CUDA(expr)                                                                       \
+  do { cudaError_t _e = (expr); if (_e != cudaSuccess) {                                        \
+      snprintf(g_isdfb_create_err, sizeof(g_isdfb_create_err), "%s -> %s", #expr, cudaGetErrorString(_e)); \
+      isdfb_destroy(ctx); return ISDFB_ERR_CUDA; } } while (0)
+
+  CREATE_CUDA(cudaSetDevice(device));
+  CREATE_CUDA(cudaMalloc(&ctx->w_packed, ctx->lay.n_packed * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&ctx->g_packed, ctx->lay.n_packed * sizeof(float)));
+  CREATE_CUDA(cudaMemset(ctx->w_packed, 0, ctx->lay.n_packed * sizeof(float)));
+  CREATE_CUDA(cudaMemset(ctx->g_packed, 0, ctx->lay.n_packed * sizeof(float)));
+  if (cfg->precision == ISDFB_PREC_FP32) {
+    simt_workspace_floats(ctx->lay, ctx->cap, &ctx->ws_floats);
+  } else {
+    ctx->ws_floats = 0;
+  }
+  ctx->ws_floats += 65536;   // K5 scratch lives at the end of the slab
+  CREATE_CUDA(cudaMalloc(&ctx->ws, ctx->ws_floats * sizeof(float)));
+  if (cfg->precision != ISDFB_PREC_FP32) {
+    rc = tc_create(ctx);
+    if (rc) { snprintf(g_isdfb_create_err, sizeof(g_isdfb_create_err), "%s", ctx->err); isdfb_destroy(ctx); return rc; }
+  }
+  *out = ctx;
+  return ISDFB_OK;
+}
+
+int isdfb_destroy(isdfb_ctx* ctx) {
+  if (!ctx) return ISDFB_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->tc) tc_destroy(ctx);
+  if (ctx->w_packed) cudaFree(ctx->w_packed);
+  if (ctx->g_packed) cudaFree(ctx->g_packed);
+  if (ctx->ws) cudaFree(ctx->ws);
+  delete ctx;
+  return ISDFB_OK;
+}
+
+const char* isdfb_last_error(const isdfb_ctx* ctx) { return ctx ? ctx->err : g_isdfb_create_err; }
+int64_t isdfb_param_count(const isdfb_ctx* ctx) { return ctx ? ctx->lay.n_flat : 0; }
+int32_t isdfb_embedding_size(const isdfb_ctx* ctx) { return ctx ? ctx->lay.E : 0; }
+int64_t isdfb_launch_count(const isdfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+#define ENTER(ctx)                                                     \
+  if (!(ctx)) return ISDFB_ERR_ARG;                                    \
+  ISDFB_CUDA_OK(ctx, cudaSetDevice((ctx)->device));                    \
+  cudaStream_t st = (cudaStream_t)stream;
+
+int isdfb_pack_weights(isdfb_ctx* ctx, const float* params_flat, void* stream) {
+  ENTER(ctx);
+  if (!params_flat) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "params_flat is null");
+  return optim_pack(ctx, params_flat, st);
+}
+
+int isdfb_gather_rays(isdfb_ctx* ctx, const float* depth, const float* normals, const int64_t* frame_map,
+                      int32_t normals_use_frame_map, const int64_t* ib, const int64_t* ih, const int64_t* iw,
+                      int64_t n_rays, const isdfb_camera* cam, float* depth_out, float* normal_out,
+                      uint8_t* valid_out, void* stream) {
+  ENTER(ctx);
+  if (!depth || !ib || !ih || !iw || !cam || !depth_out || !valid_out || (normals && !normal_out))
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_gather_rays: null argument");
+  return sample_gather(ctx, depth, normals, frame_map, normals_use_frame_map, ib, ih, iw, n_rays, cam,
+                       depth_out, normal_out, valid_out, st);
+}
+
+int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC, const int64_t* frame_map, const int64_t* ib,
+                      const int64_t* ih, const int64_t* iw, const float* depth_sample, const float* u_strat,
+                      const float* n_near, const float* lin, int64_t n_rays, int32_t n_strat, int32_t n_surf,
+                      const isdfb_camera* cam, float min_depth, float dist_behind, float* pc, float* z_vals,
+                      float* dirs_C, float* T_WC_sample, void* stream) {
+  ENTER(ctx);
+  if (!T_WC || !ib || !ih || !iw || !depth_sample || !u_strat || !lin || !cam || !pc || !z_vals || !dirs_C || !T_WC_sample)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_rays: null argument");
+  if (n_strat < 1 || n_surf < 0 || (n_surf > 1 && !n_near))
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_rays: bad sample counts (n_strat %d n_surf %d)", n_strat, n_surf);
+  return sample_along(ctx, T_WC, frame_map, ib, ih, iw, depth_sample, u_strat, n_near, lin, n_rays, n_strat,
+                      n_surf, cam, min_depth, dist_behind, pc, z_vals, dirs_C, T_WC_sample, st);
+}
+
+int isdfb_mlp_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n,
+                      float* sdf, void* stream) {
+  ENTER(ctx);
+  if (!ctx->weights_ready) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "weights not packed (call isdfb_pack_weights)");
+  if (n == 0) return ISDFB_OK;
+  if (!x || !sdf) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_mlp_forward: null argument");
+  if (ctx->cfg.precision == ISDFB_PREC_FP32) return simt_forward(ctx, x, noise, noise_std, n, sdf, nullptr, st);
+  return tc_forward(ctx, x, noise, noise_std, n, sdf, nullptr, st);
+}
+
+int isdfb_mlp_forward_grad(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n,
+                           float* sdf, float* grad, void* stream) {
+  ENTER(ctx);
+  if (!ctx->weights_ready) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "weights not packed (call isdfb_pack_weights)");
+  if (n == 0) return ISDFB_OK;
+  if (!x || !sdf || !grad) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_mlp_forward_grad: null argument");
+  if (ctx->cfg.precision == ISDFB_PREC_FP32) return simt_forward(ctx, x, noise, noise_std, n, sdf, grad, st);
+  return tc_forward(ctx, x, noise, noise_std, n, sdf, grad, st);
+}
+
+int isdfb_train_fwd_bwd(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample,
+                        const float* dirs_C, const float* T_WC_sample, const float* norm_sample,
+                        const float* noise, const uint8_t* ray_valid, int64_t n_rays, int32_t n_samples,
+                        const isdfb_loss_cfg* loss, float* sdf, float* grad, float* loss_mat,
+                        float* loss_sums, void* stream) {
+  ENTER(ctx);
+  if (!ctx->weights_ready) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "weights not packed (call isdfb_pack_weights)");
+  if (n_rays == 0) return ISDFB_OK;
+  if (!pc || !z_vals || !depth_sample || !dirs_C || !T_WC_sample || !loss || !sdf || !loss_mat || !loss_sums)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_train_fwd_bwd: null argument");
+  if (loss->grad_weight != 0.f && !norm_sample)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_train_fwd_bwd: grad_weight != 0 needs norm_sample");
+  if (loss->loss_type != 1 && loss->loss_type != 2)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "Must be L1 or L2");   // loss.py:143
+  if (n_samples < 1) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "n_samples %d", n_samples);
+  if (ctx->cfg.precision == ISDFB_PREC_FP32)
+    return simt_train(ctx, pc, z_vals, depth_sample, dirs_C, T_WC_sample, norm_sample, noise, ray_valid, n_rays,
+                      n_samples, loss, sdf, grad, loss_mat, loss_sums, st);
+  return tc_train(ctx, pc, z_vals, depth_sample, dirs_C, T_WC_sample, norm_sample, noise, ray_valid, n_rays,
+                  n_samples, loss, sdf, grad, loss_mat, loss_sums, st);
+}
+
+int isdfb_zero_grad(isdfb_ctx* ctx, void* stream) {
+  ENTER(ctx);
+  ISDFB_CUDA_OK(ctx, cudaMemsetAsync(ctx->g_packed, 0, ctx->lay.n_packed * sizeof(float), st));
+  return ISDFB_OK;
+}
+
+int isdfb_export_grads(isdfb_ctx* ctx, float* grads_flat, void* stream) {
+  ENTER(ctx);
+  if (!grads_flat) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "grads_flat is null");
+  return optim_export_grads(ctx, grads_flat, st);
+}
+
+int isdfb_frame_bins(isdfb_ctx* ctx, const float* loss_mat, const uint8_t* ray_valid, const int64_t* ib,
+                     const int64_t* ih, const int64_t* iw, int64_t n_rays, int32_t n_samples, int32_t n_frames,
+                     int32_t H, int32_t W, int32_t factor, float* loss_approx, float* frame_avg, void* stream) {
+  ENTER(ctx);
+  if (!loss_approx || !frame_avg || (n_rays > 0 && (!loss_mat || !ib || !ih || !iw)))
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_frame_bins: null argument");
+  if (factor < 1 || H % factor || W % factor)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "H (%d) and W (%d) must be divisible by factor %d (loss.py:209-211)", H, W, factor);
+  if ((int64_t)n_frames * factor * factor * 2 > 65536)
+    ISDFB_FAIL(ctx, ISDFB_ERR_CAPACITY, "too many frames (%d) for the histogram scratch", n_frames);
+  return sample_frame_bins(ctx, g_scratch_of(ctx), loss_mat, ray_valid, ib, ih, iw, n_rays, n_samples, n_frames,
+                           H, W, factor, loss_approx, frame_avg, st);
+}
+
+int isdfb_adamw(isdfb_ctx* ctx, float* params_flat, float* m, float* v, int64_t step, float lr, float beta1,
+                float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+  ENTER(ctx);
+  if (!params_flat || !m || !v || step < 1) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_adamw: bad argument");
+  return optim_adamw(ctx, params_flat, m, v, step, lr, beta1, beta2, eps, weight_decay, grad_scale, st);
+}
+
+int isdfb_grad_buffer(isdfb_ctx* ctx, float** ptr, int64_t* n_floats) {
+  if (!ctx || !ptr || !n_floats) return ISDFB_ERR_ARG;
+  *ptr = ctx->g_packed;
+  *n_floats = ctx->lay.n_packed;
+  return ISDFB_OK;
+}
+
+}  // extern "C"
+
+static float* g_scratch_of(isdfb_ctx* ctx) { return ctx->ws + (ctx->ws_floats - 65536); }
