@@ -63,6 +63,7 @@ typedef struct {
   int32_t loss_type;         /* 1 = L1, 2 = L2                                   */
   float noise_std;           /* SDFMap.forward noise_std (0 = none)              */
   float inv_count;           /* 1 / (number of valid samples the mean runs over) */
+  const float* inv_count_dev;/* optional DEVICE scalar overriding inv_count (no host sync on the count) */
 } isdfb_loss_cfg;
 
 /* Camera intrinsics: transform.py:13-33 (ray_dirs_C, depth_type 'z'). */
@@ -94,7 +95,10 @@ int isdfb_pack_weights(isdfb_ctx* ctx, const float* params_flat, void* stream);
  * isdfb_sample_rays   = transform.origin_dirs_W + sample.stratified_sample +
  *   sample.sample_along_rays (transform.py:36-41, sample.py:77-178) for already-compacted rays:
  *   z = [depth, clamp(depth+n_near, min_depth, depth+dist_behind), strat bins]; pc = o + d_W z.
- *   `lin` is torch.linspace(0,1,n_strat+1) (passed in so bin edges are bit-identical).       */
+ *   `lin` is torch.linspace(0,1,n_strat+1) (passed in so bin edges are bit-identical).
+ *   ib == NULL: T_WC is already per ray ([R,4,4]).  dirs_C_in != NULL: use these camera-frame
+ *   directions instead of recomputing them from (ih, iw).  far != NULL: per-ray far limit
+ *   (the reference's max_depth tensor) instead of depth + dist_behind.                         */
 int isdfb_gather_rays(isdfb_ctx* ctx, const float* depth, const float* normals,
                       const int64_t* frame_map, int32_t normals_use_frame_map,
                       const int64_t* ib, const int64_t* ih, const int64_t* iw, int64_t n_rays,
@@ -102,11 +106,17 @@ int isdfb_gather_rays(isdfb_ctx* ctx, const float* depth, const float* normals,
                       uint8_t* valid_out, void* stream);
 int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC /*[F,4,4]*/, const int64_t* frame_map,
                       const int64_t* ib, const int64_t* ih, const int64_t* iw,
-                      const float* depth_sample, const float* u_strat, const float* n_near,
+                      const float* dirs_C_in, const float* depth_sample, const float* far,
+                      const float* u_strat, const float* n_near,
                       const float* lin, int64_t n_rays, int32_t n_strat, int32_t n_surf,
                       const isdfb_camera* cam, float min_depth, float dist_behind,
                       float* pc /*[R,S,3]*/, float* z_vals /*[R,S]*/, float* dirs_C /*[R,3]*/,
                       float* T_WC_sample /*[R,4,4]*/, void* stream);
+
+/* ---- positional encoding alone -----------------------------------------------------------
+ * PostionalEncoding.forward (embedding.py:95-111): out[n, E] row-major.  The training and
+ * inference kernels never materialise this tensor; the entry exists for API parity.        */
+int isdfb_pe_encode(isdfb_ctx* ctx, const float* x, int64_t n, float* out, void* stream);
 
 /* ---- K2 / K3: PE + MLP forward, and forward + input gradient --------------------------
  * isdfb_mlp_forward       = SDFMap.forward (fc_map.py:94-111) incl. noise and scale_output.

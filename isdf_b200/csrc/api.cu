@@ -7,7 +7,7 @@ char g_isdfb_create_err[512] = "";
 int sample_gather(isdfb_ctx*, const float*, const float*, const int64_t*, int, const int64_t*, const int64_t*,
                   const int64_t*, int64_t, const isdfb_camera*, float*, float*, uint8_t*, cudaStream_t);
 int sample_along(isdfb_ctx*, const float*, const int64_t*, const int64_t*, const int64_t*, const int64_t*,
-                 const float*, const float*, const float*, const float*, int64_t, int, int,
+                 const float*, const float*, const float*, const float*, const float*, const float*, int64_t, int, int,
                  const isdfb_camera*, float, float, float*, float*, float*, float*, cudaStream_t);
 int sample_frame_bins(isdfb_ctx*, float*, const float*, const uint8_t*, const int64_t*, const int64_t*,
                       const int64_t*, int64_t, int, int, int, int, int, float*, float*, cudaStream_t);
@@ -139,6 +139,7 @@ int isdfb_gather_rays(isdfb_ctx* ctx, const float* depth, const float* normals, 
                       int64_t n_rays, const isdfb_camera* cam, float* depth_out, float* normal_out,
                       uint8_t* valid_out, void* stream) {
   ENTER(ctx);
+  if (n_rays == 0) return ISDFB_OK;
   if (!depth || !ib || !ih || !iw || !cam || !depth_out || !valid_out || (normals && !normal_out))
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_gather_rays: null argument");
   return sample_gather(ctx, depth, normals, frame_map, normals_use_frame_map, ib, ih, iw, n_rays, cam,
@@ -146,17 +147,25 @@ int isdfb_gather_rays(isdfb_ctx* ctx, const float* depth, const float* normals, 
 }
 
 int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC, const int64_t* frame_map, const int64_t* ib,
-                      const int64_t* ih, const int64_t* iw, const float* depth_sample, const float* u_strat,
-                      const float* n_near, const float* lin, int64_t n_rays, int32_t n_strat, int32_t n_surf,
+                      const int64_t* ih, const int64_t* iw, const float* dirs_C_in, const float* depth_sample,
+                      const float* far, const float* u_strat, const float* n_near, const float* lin, int64_t n_rays, int32_t n_strat, int32_t n_surf,
                       const isdfb_camera* cam, float min_depth, float dist_behind, float* pc, float* z_vals,
                       float* dirs_C, float* T_WC_sample, void* stream) {
   ENTER(ctx);
-  if (!T_WC || !ib || !ih || !iw || !depth_sample || !u_strat || !lin || !cam || !pc || !z_vals || !dirs_C || !T_WC_sample)
+  if (n_rays == 0) return ISDFB_OK;
+  if (!T_WC || (!dirs_C_in && (!ih || !iw)) || !depth_sample || !u_strat || !lin || !cam || !pc || !z_vals || !dirs_C || !T_WC_sample)
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_rays: null argument");
   if (n_strat < 1 || n_surf < 0 || (n_surf > 1 && !n_near))
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_rays: bad sample counts (n_strat %d n_surf %d)", n_strat, n_surf);
-  return sample_along(ctx, T_WC, frame_map, ib, ih, iw, depth_sample, u_strat, n_near, lin, n_rays, n_strat,
+  return sample_along(ctx, T_WC, frame_map, ib, ih, iw, dirs_C_in, depth_sample, far, u_strat, n_near, lin, n_rays, n_strat,
                       n_surf, cam, min_depth, dist_behind, pc, z_vals, dirs_C, T_WC_sample, st);
+}
+
+int isdfb_pe_encode(isdfb_ctx* ctx, const float* x, int64_t n, float* out, void* stream) {
+  ENTER(ctx);
+  if (n == 0) return ISDFB_OK;
+  if (!x || !out) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_pe_encode: null argument");
+  return simt_pe_encode(ctx, x, n, out, st);
 }
 
 int isdfb_mlp_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n,

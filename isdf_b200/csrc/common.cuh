@@ -92,6 +92,7 @@ int simt_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float
                const float* noise, const uint8_t* ray_valid, int64_t n_rays, int32_t S,
                const isdfb_loss_cfg* loss, float* sdf, float* grad, float* loss_mat,
                float* loss_sums, cudaStream_t st);
+int simt_pe_encode(isdfb_ctx* ctx, const float* x, int64_t n, float* out, cudaStream_t st);
 int optim_pack(isdfb_ctx* ctx, const float* params_flat, cudaStream_t st);
 int optim_adamw(isdfb_ctx* ctx, float* params_flat, float* m, float* v, int64_t step, float lr,
                 float b1, float b2, float eps, float wd, float grad_scale, cudaStream_t st);

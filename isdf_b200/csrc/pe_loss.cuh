@@ -57,7 +57,7 @@ struct LossPoint {
 __device__ __forceinline__ LossPoint loss_point(const isdfb_loss_cfg& c, float sdf, const float g[3],
                                                 float bnd, const float u[3]) {
   LossPoint o;
-  const float inv_n = c.inv_count;
+  const float inv_n = c.inv_count_dev ? __ldg(c.inv_count_dev) : c.inv_count;
   // free-space / truncation SDF loss (loss.py:122-164)
   float relu_t = fmaxf(sdf - bnd, 0.f);
   float ex = expf(-5.0f * sdf);

@@ -31,7 +31,8 @@ __global__ void gather_rays_kernel(const float* __restrict__ depth, const float*
 // one thread per (ray, sample)
 __global__ void sample_rays_kernel(const float* __restrict__ T_WC, const int64_t* __restrict__ frame_map,
                                    const int64_t* __restrict__ ib, const int64_t* __restrict__ ih,
-                                   const int64_t* __restrict__ iw, const float* __restrict__ depth_s,
+                                   const int64_t* __restrict__ iw, const float* __restrict__ dirs_in,
+                                   const float* __restrict__ depth_s, const float* __restrict__ far_in,
                                    const float* __restrict__ u_strat, const float* __restrict__ n_near,
                                    const float* __restrict__ lin, int64_t n_rays, int n_strat, int n_surf,
                                    isdfb_camera cam, float min_depth, float dist_behind,
@@ -42,19 +43,23 @@ __global__ void sample_rays_kernel(const float* __restrict__ T_WC, const int64_t
   if (i >= n_rays * S) return;
   int64_t r = i / S;
   int j = (int)(i - r * S);
-  int64_t b = ib[r];
+  int64_t b = ib ? ib[r] : r;            // ib == NULL: T_WC is already per ray
   int64_t f = frame_map ? frame_map[b] : b;
   const float* T = T_WC + f * 16;
-  // camera-frame direction (transform.py:13-33, depth_type 'z')
-  float dx = __fdiv_rn(__fsub_rn((float)iw[r], cam.cx), cam.fx);
-  float dy = __fdiv_rn(__fsub_rn((float)ih[r], cam.cy), cam.fy);
-  float dz = 1.0f;
+  float dx, dy, dz;
+  if (dirs_in) {
+    dx = dirs_in[r * 3]; dy = dirs_in[r * 3 + 1]; dz = dirs_in[r * 3 + 2];
+  } else {                               // camera-frame direction (transform.py:13-33, depth_type 'z')
+    dx = __fdiv_rn(__fsub_rn((float)iw[r], cam.cx), cam.fx);
+    dy = __fdiv_rn(__fsub_rn((float)ih[r], cam.cy), cam.fy);
+    dz = 1.0f;
+  }
   // world-frame direction (transform.py:36-41)
   float wx = __fadd_rn(__fadd_rn(__fmul_rn(T[0], dx), __fmul_rn(T[1], dy)), __fmul_rn(T[2], dz));
   float wy = __fadd_rn(__fadd_rn(__fmul_rn(T[4], dx), __fmul_rn(T[5], dy)), __fmul_rn(T[6], dz));
   float wz = __fadd_rn(__fadd_rn(__fmul_rn(T[8], dx), __fmul_rn(T[9], dy)), __fmul_rn(T[10], dz));
   float d = depth_s[r];
-  float far = __fadd_rn(d, dist_behind);
+  float far = far_in ? far_in[r] : __fadd_rn(d, dist_behind);
   float z;
   if (j < n_surf) {
     if (j == 0) {
@@ -141,14 +146,15 @@ int sample_gather(isdfb_ctx* ctx, const float* depth, const float* normals, cons
 }
 
 int sample_along(isdfb_ctx* ctx, const float* T_WC, const int64_t* frame_map, const int64_t* ib,
-                 const int64_t* ih, const int64_t* iw, const float* depth_sample, const float* u_strat,
+                 const int64_t* ih, const int64_t* iw, const float* dirs_in, const float* depth_sample,
+                 const float* far_in, const float* u_strat,
                  const float* n_near, const float* lin, int64_t n_rays, int n_strat, int n_surf,
                  const isdfb_camera* cam, float min_depth, float dist_behind, float* pc, float* z_vals,
                  float* dirs_C, float* T_out, cudaStream_t st) {
   if (n_rays == 0) return ISDFB_OK;
   int64_t total = n_rays * (n_strat + n_surf);
   sample_rays_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      T_WC, frame_map, ib, ih, iw, depth_sample, u_strat, n_near, lin, n_rays, n_strat, n_surf, *cam,
+      T_WC, frame_map, ib, ih, iw, dirs_in, depth_sample, far_in, u_strat, n_near, lin, n_rays, n_strat, n_surf, *cam,
       min_depth, dist_behind, pc, z_vals, dirs_C, T_out);
   ISDFB_LAUNCHED(ctx);
   ISDFB_CUDA_OK(ctx, cudaGetLastError());

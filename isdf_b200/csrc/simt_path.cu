@@ -455,6 +455,14 @@ static void simt_s1_s2(isdfb_ctx* ctx, const SimtWs& w, const float* x, const fl
   ISDFB_LAUNCHED(ctx);
 }
 
+int simt_pe_encode(isdfb_ctx* ctx, const float* x, int64_t n, float* out, cudaStream_t st) {
+  const int E = ctx->lay.E;
+  pe_kernel<<<nblk(n * E, 256), 256, 0, st>>>(ctx->pe, x, n, n, E, E, out);
+  ISDFB_LAUNCHED(ctx);
+  ISDFB_CUDA_OK(ctx, cudaGetLastError());
+  return ISDFB_OK;
+}
+
 int simt_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n,
                  float* sdf, float* grad, cudaStream_t st) {
   SimtWs w = carve(ctx);

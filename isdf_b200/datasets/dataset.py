@@ -1,0 +1,86 @@
+"""Posed-depth sources for the Trainer.
+
+`SyntheticStream` is the seeded synthetic stream of SURVEY.md 8d (the real sequences are not
+available offline); `ReplicaDataset` reads the reference's ReplicaCAD on-disk layout
+(reference isdf/datasets/dataset.py:20-71: results/depth%06d.png, frame%06d.png, traj.txt)."""
+import math
+import os
+
+import numpy as np
+
+
+class SyntheticStream:
+    """Frame k: depth[v,u] = 2 + 0.5 sin(u/80 + 0.1k) + 0.3 cos(v/60) metres, small yaw + translation."""
+
+    def __init__(self, n_frames, H, W, invalid_frac=0.0, seed=1234, depth_scale=1000.0, rot=True):
+        self.n_frames, self.H, self.W = n_frames, H, W
+        self.invalid_frac, self.seed, self.depth_scale, self.rot = invalid_frac, seed, depth_scale, rot
+        v = np.arange(H, dtype=np.float32)[:, None]
+        u = np.arange(W, dtype=np.float32)[None, :]
+        self._v_term = (0.3 * np.cos(v / 60.0)).astype(np.float32)
+        self._u = u
+
+    def __len__(self):
+        return self.n_frames
+
+    def pose(self, k):
+        T = np.eye(4, dtype=np.float32)
+        if self.rot:
+            a = 0.05 * k
+            c, s = math.cos(a), math.sin(a)
+            T[0, 0], T[0, 2], T[2, 0], T[2, 2] = c, s, -s, c
+        T[0, 3], T[1, 3] = 0.05 * k, 0.01 * k
+        return T
+
+    def depth(self, k):
+        d = (2.0 + 0.5 * np.sin(self._u / 80.0 + 0.1 * k) + self._v_term).astype(np.float32)
+        if self.invalid_frac > 0:
+            rng = np.random.default_rng(self.seed + k)
+            d[rng.random((self.H, self.W)) < self.invalid_frac] = 0.0
+        return d
+
+    def __getitem__(self, k):
+        k = int(k) % self.n_frames
+        image = np.full((self.H, self.W, 3), 128, dtype=np.uint8)
+        return {"image": image, "depth": self.depth(k), "T": self.pose(k)}
+
+
+class ReplicaDataset:
+    def __init__(self, root_dir, traj_file=None, rgb_transform=None, depth_transform=None, noisy_depth=False,
+                 col_ext=".jpg", distortion_coeffs=None, camera_matrix=None):
+        self.Ts = None if traj_file is None else np.loadtxt(traj_file).reshape(-1, 4, 4)
+        self.root_dir = root_dir
+        self.rgb_transform, self.depth_transform = rgb_transform, depth_transform
+        self.col_ext, self.noisy_depth = col_ext, noisy_depth
+
+    def __len__(self):
+        return self.Ts.shape[0]
+
+    def __getitem__(self, idx):
+        import cv2
+        s = "%06d" % int(idx)
+        depth_file = os.path.join(self.root_dir, ("ndepth" if self.noisy_depth else "depth") + s + ".png")
+        rgb_file = os.path.join(self.root_dir, "frame" + s + self.col_ext)
+        depth = cv2.imread(depth_file, -1)
+        image = cv2.imread(rgb_file)
+        if depth is None or image is None:
+            raise FileNotFoundError("missing frame %s under %s" % (s, self.root_dir))
+        T = self.Ts[idx] if self.Ts is not None else None
+        if self.rgb_transform:
+            image = self.rgb_transform(image)
+        if self.depth_transform:
+            depth = self.depth_transform(depth)
+        return {"image": image, "depth": depth, "T": T}
+
+
+def depth_scale_filter(inv_scale, max_depth):
+    """uint16 depth -> metres, far values zeroed (reference datasets/image_transforms.py:18-38)."""
+    def f(depth):
+        d = depth.astype(np.float32) * inv_scale
+        d[d > max_depth] = 0.0
+        return d
+    return f
+
+
+def bgr_to_rgb(image):
+    return image[:, :, ::-1].copy()

@@ -63,6 +63,9 @@ class Engine:
         self.n_params = int(self.lib.isdfb_param_count(self._ctx))
         self.embedding_size = int(self.lib.isdfb_embedding_size(self._ctx))
 
+    def __deepcopy__(self, memo):
+        return None          # contexts are not copyable; owners re-create them lazily
+
     def __del__(self):
         try:
             if getattr(self, "_ctx", None) is not None and self._ctx.value:
@@ -106,16 +109,18 @@ class Engine:
         return d_out, n_out, valid
 
     def sample_rays(self, T_WC, ib, ih, iw, depth_sample, u_strat, n_near, lin, n_strat, n_surf, cam,
-                    min_depth, dist_behind, frame_map=None):
+                    min_depth, dist_behind, frame_map=None, dirs_C_in=None, far=None):
         dev = self.device
         T_WC = _f32(T_WC, "T_WC", dev)
         ib, ih, iw = _i64(ib, "indices_b", dev), _i64(ih, "indices_h", dev), _i64(iw, "indices_w", dev)
+        dirs_C_in = _f32(dirs_C_in, "dirs_C", dev)
+        far = _f32(far, "max_depth", dev)
         frame_map = _i64(frame_map, "frame_map", dev)
         depth_sample = _f32(depth_sample, "depth_sample", dev)
         u_strat = _f32(u_strat, "u_strat", dev)
         n_near = _f32(n_near, "n_near", dev)
         lin = _f32(lin, "lin", dev)
-        R = ib.numel()
+        R = depth_sample.numel()
         S = n_strat + n_surf
         if u_strat.shape != (R, n_strat):
             raise ValueError("u_strat must be [%d,%d]" % (R, n_strat))
@@ -126,11 +131,18 @@ class Engine:
         dirs_C = torch.empty(R, 3, dtype=torch.float32, device=dev)
         T_s = torch.empty(R, 4, 4, dtype=torch.float32, device=dev)
         self._ck(self.lib.isdfb_sample_rays(self._ctx, _ptr(T_WC), _ptr(frame_map), _ptr(ib), _ptr(ih), _ptr(iw),
-                                            _ptr(depth_sample), _ptr(u_strat), _ptr(n_near), _ptr(lin), R,
+                                            _ptr(dirs_C_in), _ptr(depth_sample), _ptr(far), _ptr(u_strat), _ptr(n_near), _ptr(lin), R,
                                             int(n_strat), int(n_surf), C.byref(cam), float(min_depth),
                                             float(dist_behind), _ptr(pc), _ptr(z), _ptr(dirs_C), _ptr(T_s),
                                             self._stream()))
         return pc, z, dirs_C, T_s
+
+    def pe_encode(self, x):
+        x = _f32(x, "x", self.device)
+        n = x.numel() // 3
+        out = torch.empty(*x.shape[:-1], self.embedding_size, dtype=torch.float32, device=self.device)
+        self._ck(self.lib.isdfb_pe_encode(self._ctx, _ptr(x), n, _ptr(out), self._stream()))
+        return out
 
     # ---- K2 / K3 -----------------------------------------------------
     def forward(self, x, noise=None, noise_std=0.0, want_grad=False):
@@ -227,7 +239,7 @@ class _DevView:
 
 
 def make_loss_cfg(trunc_weight, trunc_distance, eik_weight, eik_apply_dist, grad_weight, orien_loss, loss_type,
-                  noise_std, inv_count):
+                  noise_std, inv_count, inv_count_dev=None):
     lc = _lib.LossCfg()
     lc.trunc_weight, lc.trunc_distance = float(trunc_weight), float(trunc_distance)
     lc.eik_weight, lc.eik_apply_dist = float(eik_weight), float(eik_apply_dist)
@@ -238,6 +250,12 @@ def make_loss_cfg(trunc_weight, trunc_distance, eik_weight, eik_apply_dist, grad
     lc.loss_type = 1 if loss_type == "L1" else 2
     lc.noise_std = float(noise_std or 0.0)
     lc.inv_count = float(inv_count)
+    lc.inv_count_dev = None
+    if inv_count_dev is not None:
+        if inv_count_dev.dtype != torch.float32 or not inv_count_dev.is_cuda:
+            raise TypeError("inv_count_dev must be a float32 CUDA scalar")
+        lc.inv_count_dev = inv_count_dev.data_ptr()
+        lc._keepalive = inv_count_dev
     return lc
 
 

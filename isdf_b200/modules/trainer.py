@@ -1,0 +1,512 @@
+"""Trainer -- host-side mirror of reference isdf/modules/trainer.py for the training hot path.
+
+Same constructor, attributes and method names the reference drivers use (train.py, train_vis.py,
+batch_train): Trainer(device, config_file, chkpt_load_file, incremental, grid_dim); step() ->
+(losses, step_time_ms); get_data / add_frame / check_keyframe_latest / select_keyframes /
+sample_points / sdf_eval_and_loss.  One step launches (reference trainer.py:951-1016):
+
+    K1 isdfb_gather_rays + isdfb_sample_rays      (sample.py, transform.py)
+    K4 isdfb_train_fwd_bwd                        (embedding.py, fc_map.py, loss.py, backward())
+    K5 isdfb_frame_bins                           (loss.frame_avg)
+    C1 one NCCL all-reduce of the flat gradient   (new: data-parallel keyframe shards)
+    K6 isdfb_adamw                                (optim.AdamW.step + weight re-pack)
+
+Two RNG modes: "reference" consumes torch / numpy generators in exactly the reference's order
+(one host sync for the data-dependent ray compaction, as in the reference);
+"fast" keeps fixed shapes with a validity mask and never synchronises inside the step.
+Visualisation, evaluation and mesh extraction are out of scope and raise.
+"""
+import copy
+import json
+import os
+
+import numpy as np
+import torch
+
+from .. import DEFAULT_PRECISION
+from ..datasets import dataset as ds
+from ..datasets.data_util import FrameData
+from ..engine import make_camera, make_loss_cfg
+from ..eval.metrics import start_timing, end_timing
+from ..geometry import transform
+from . import embedding, fc_map, render, sample
+
+_OUT_OF_SCOPE = ("view_sdf", "latest_frame_vis", "update_vis_vars", "frames_vis", "draw_3D", "draw_obj_3D",
+                 "obj_slices_vis", "write_slices", "write_mesh", "mesh_rec", "eval_fixed", "eval_sdf",
+                 "eval_object_sdf", "eval_mesh", "compute_slices", "sdf_fn", "grad_fn")
+
+
+class FusedAdamW:
+    """torch.optim.AdamW-compatible facade over K6 (flat parameters, fused re-pack)."""
+
+    def __init__(self, sdf_map, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8):
+        self.sdf_map = sdf_map
+        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.param_groups = [dict(self.defaults, params=list(sdf_map.parameters()))]
+        self.step_count = 0
+        self.exp_avg = None
+        self.exp_avg_sq = None
+
+    def _state(self):
+        flat = self.sdf_map.flat_parameters()
+        if self.exp_avg is None or self.exp_avg.device != flat.device:
+            self.exp_avg = torch.zeros_like(flat)
+            self.exp_avg_sq = torch.zeros_like(flat)
+        return flat
+
+    def step(self, grad_scale=1.0):
+        eng = self.sdf_map.engine()
+        flat = self._state()
+        g = self.param_groups[0]
+        self.step_count += 1
+        eng.adamw(flat, self.exp_avg, self.exp_avg_sq, self.step_count, g["lr"], g["betas"][0], g["betas"][1],
+                  g["eps"], g["weight_decay"], grad_scale)
+        self.sdf_map.mark_packed()
+
+    def zero_grad(self, set_to_none=True):
+        self.sdf_map.engine().zero_grad()
+
+    def state_dict(self):
+        self._state()
+        state, off = {}, 0
+        for i, p in enumerate(self.sdf_map.parameters()):
+            n = p.numel()
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+            off += n
+        groups = [dict({k: v for k, v in self.param_groups[0].items() if k != "params"},
+                       params=list(range(len(state))))]
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        self._state()
+        off = 0
+        for i, p in enumerate(self.sdf_map.parameters()):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + n] = st["exp_avg"].reshape(-1).to(self.exp_avg.device)
+                self.exp_avg_sq[off:off + n] = st["exp_avg_sq"].reshape(-1).to(self.exp_avg.device)
+                self.step_count = int(float(st["step"]))
+            off += n
+
+
+class Trainer:
+    def __init__(self, device, config_file, chkpt_load_file=None, incremental=True, grid_dim=200,
+                 precision=None, rng_mode=None, rng_device=None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("isdf_b200.Trainer needs a CUDA device (got %s); there is no CPU path" % device)
+        self.incremental = incremental
+        self.tot_step_time = 0.
+        self.last_is_keyframe = False
+        self.steps_since_frame = 0
+        self.optim_frames = 0
+        self.gt_depth_vis = self.gt_im_vis = None
+        self.gt_sdf_interp = self.stage_sdf_interp = self.sdf_dims = self.sdf_transform = None
+        self.grid_dim, self.new_grid_dim, self.chunk_size = grid_dim, None, 100000
+        if isinstance(config_file, dict):
+            self.config = copy.deepcopy(config_file)
+        else:
+            with open(config_file) as f:
+                self.config = json.load(f)
+        b200 = self.config.get("b200", {})
+        self.precision = precision or b200.get("precision") or os.environ.get("ISDFB_PRECISION", DEFAULT_PRECISION)
+        self.rng_mode = rng_mode or b200.get("rng_mode", "reference")
+        if self.rng_mode not in ("reference", "fast"):
+            raise ValueError("rng_mode must be 'reference' or 'fast'")
+        self.rng_device = rng_device            # e.g. 'cpu' to replay a CPU run of the reference
+        self.fix_normal_window = bool(b200.get("fix_normal_window", 0))
+        self.max_points = int(b200.get("max_points", 32768))
+        self.dist_world, self.dist_rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.dist_world, self.dist_rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+
+        self.frames = FrameData()
+        self.set_params()
+        self.set_cam()
+        self.load_data()
+        self.scene_center = None
+        self.inv_bounds_transform = None
+        self.active_idxs = None
+        self.active_pixels = None
+        if self.gt_scene:
+            raise NotImplementedError("configs with gt_sdf_dir need the GT mesh tool-chain (trimesh), which is out "
+                                      "of scope; drop dataset.gt_sdf_dir or set Trainer.inv_bounds_transform")
+        self.load_networks()
+        if chkpt_load_file is not None:
+            self.load_checkpoint(chkpt_load_file)
+        self.sdf_map.train()
+        self.cosSim = torch.nn.CosineSimilarity(dim=-1, eps=1e-6)
+        self._loss_sums = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._lin_cache = {}
+
+    def __getattr__(self, name):
+        if name in _OUT_OF_SCOPE:
+            def _raise(*a, **k):
+                raise NotImplementedError("Trainer.%s is visualisation / evaluation code outside the hot path "
+                                          "(SURVEY.md section 2); use the reference implementation for it" % name)
+            return _raise
+        raise AttributeError(name)
+
+    # ---- configuration (trainer.py:157-333) ------------------------------------------------
+    def get_latest_frame_id(self):
+        return int(self.tot_step_time * self.fps)
+
+    def set_params(self):
+        cfg = self.config
+        d = cfg["dataset"]
+        self.dataset_format = d["format"]
+        self.live = self.dataset_format in ("arkit", "realsense", "realsense_franka")
+        if self.live:
+            raise NotImplementedError("live (ROS / ARKit) ingest is out of scope")
+        self.ext_calib = cfg.get("ext_calib") if "realsense_franka" in self.dataset_format else None
+        self.inv_depth_scale = 1. / d["depth_scale"]
+        self.distortion_coeffs = []
+        if self.dataset_format == "ScanNet":
+            self.set_scannet_cam_params(d["intrinsics_file"])
+        else:
+            cam = d["camera"]
+            self.fx, self.fy, self.cx, self.cy = cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+            self.H, self.W = cam["h"], cam["w"]
+            self.distortion_coeffs = [cam[k] for k in ("k1", "k2", "p1", "p2", "k3") if k in cam]
+        self.gt_scene = False
+        self.fps = d.get("fps", 30)
+        self.seq_dir = d.get("seq_dir", "")
+        self.seq = ([x for x in self.seq_dir.split('/') if x != ''] or ["synthetic"])[-1]
+        self.ims_file = self.seq_dir
+        if self.dataset_format != "realsense_franka_offline":
+            self.ims_file = os.path.join(self.ims_file, "results")
+        self.obj_bounds_file = None
+        self.gt_sdf_file = None
+        self.scene_file = None
+        if "gt_sdf_dir" in d:
+            self.gt_scene = True
+            self.scene_file = d["gt_sdf_dir"] + "mesh.obj"
+            self.gt_sdf_file = d["gt_sdf_dir"] + "/1cm/sdf.npy"
+        self.scannet_dir = d.get("scannet_dir")
+        self.indices = d.get("im_indices")
+        self.noisy_depth = bool(d.get("noisy_depth", 0))
+        self.traj_file = self.seq_dir + "/traj.txt"
+        self.gt_traj = None
+        self.n_steps = cfg["trainer"]["steps"]
+
+        m = cfg["model"]
+        self.do_active = bool(m["do_active"])
+        for key in ("scale_output", "noise_std", "noise_kf", "noise_frame", "window_size", "hidden_layers_block",
+                    "hidden_feature_size", "frac_time_perception", "iters_per_kf", "iters_per_frame", "kf_dist_th",
+                    "kf_pixel_ratio"):
+            setattr(self, key, m[key])
+        emb = m["embedding"]
+        self.scale_input, self.n_embed_funcs = emb["scale_input"], emb["n_embed_funcs"]
+        self.gauss_embed, self.gauss_embed_std = bool(emb["gauss_embed"]), emb["gauss_embed_std"]
+        self.optim_embedding = bool(emb["optim_embedding"])
+        if self.gauss_embed or self.optim_embedding:
+            raise NotImplementedError("gaussian / optimised embeddings are not used by any shipped config")
+
+        ev = cfg["eval"]
+        self.do_vox_comparison = bool(ev["do_vox_comparison"]) and "eval_pts_root" in ev and False
+        self.do_eval, self.eval_freq_s = ev["do_eval"], ev["eval_freq_s"]
+        self.sdf_eval, self.mesh_eval = bool(ev["sdf_eval"]), bool(ev["mesh_eval"])
+        self.eval_times = []
+        sv = cfg["save"]
+        self.save_period = sv["save_period"]
+        self.save_times = np.arange(self.save_period, 2000, self.save_period).tolist()
+        self.save_checkpoints, self.save_slices, self.save_meshes = (bool(sv["save_checkpoints"]),
+                                                                      bool(sv["save_slices"]), bool(sv["save_meshes"]))
+        ls = cfg["loss"]
+        self.bounds_method = ls["bounds_method"]
+        assert self.bounds_method in ["ray", "normal", "pc"]
+        self.loss_type = ls["loss_type"]
+        assert self.loss_type in ["L1", "L2"]
+        for key in ("trunc_weight", "trunc_distance", "eik_weight", "eik_apply_dist", "grad_weight"):
+            setattr(self, key, ls[key])
+        self.orien_loss = bool(ls["orien_loss"])
+        self.do_normal = self.bounds_method == "normal" or self.grad_weight != 0
+        self.learning_rate, self.weight_decay = cfg["optimiser"]["lr"], cfg["optimiser"]["weight_decay"]
+        sp = cfg["sample"]
+        self.min_depth, self.max_depth = sp["depth_range"]
+        self.dist_behind_surf = sp["dist_behind_surf"]
+        self.n_rays, self.n_rays_is_kf = sp["n_rays"], sp["n_rays_is_kf"]
+        self.n_strat_samples, self.n_surf_samples = sp["n_strat_samples"], sp["n_surf_samples"]
+
+    def set_scannet_cam_params(self, file):
+        info = dict(line.split(' = ') for line in open(file).read().splitlines() if ' = ' in line)
+        self.fx, self.fy = float(info['fx_depth']), float(info['fy_depth'])
+        self.cx, self.cy = float(info['mx_depth']), float(info['my_depth'])
+        self.H, self.W = int(info['depthHeight']), int(info['depthWidth'])
+
+    def set_cam(self):
+        for tag, f in (("vis", 16), ("vis_up", 8)):
+            setattr(self, "H_" + tag, self.H // f)
+            setattr(self, "W_" + tag, self.W // f)
+            for k in ("fx", "fy", "cx", "cy"):
+                setattr(self, k + "_" + tag, getattr(self, k) / f)
+        self.loss_approx_factor = 8
+        if self.H % self.loss_approx_factor or self.W % self.loss_approx_factor:
+            raise ValueError("H and W must be divisible by %d (loss.py:209-211)" % self.loss_approx_factor)
+        self.cam = make_camera(self.fx, self.fy, self.cx, self.cy, self.H, self.W)
+        self._dirs_C = None
+
+    @property
+    def dirs_C(self):
+        """[1,H,W,3] camera directions (trainer.py:383-394); built on demand -- the kernels do not read it."""
+        if self._dirs_C is None:
+            self._dirs_C = transform.ray_dirs_C(1, self.H, self.W, self.fx, self.fy, self.cx, self.cy, self.device)
+        return self._dirs_C
+
+    def set_directions(self):
+        self._dirs_C = None
+
+    def load_networks(self):
+        pe = embedding.PostionalEncoding(min_deg=0, max_deg=self.n_embed_funcs, scale=self.scale_input,
+                                         transform=self.inv_bounds_transform)
+        self.sdf_map = fc_map.SDFMap(pe, hidden_size=self.hidden_feature_size,
+                                     hidden_layers_block=self.hidden_layers_block,
+                                     scale_output=self.scale_output).to(self.device)
+        self.sdf_map.precision = self.precision
+        self.sdf_map.max_points = self.max_points
+        self.optimiser = FusedAdamW(self.sdf_map, lr=self.learning_rate, weight_decay=self.weight_decay)
+
+    def load_checkpoint(self, checkpoint_load_file):
+        chk = torch.load(checkpoint_load_file, map_location=self.device)
+        self.sdf_map.load_state_dict(chk["model_state_dict"])
+
+    # ---- data (trainer.py:447-582) ----------------------------------------------------------
+    def load_data(self):
+        fmt = self.dataset_format
+        depth_tf = ds.depth_scale_filter(self.inv_depth_scale, self.max_depth)
+        self.up = np.array([0., 1., 0.])
+        if fmt == "synthetic":
+            d = self.config["dataset"]
+            self.scene_dataset = ds.SyntheticStream(d.get("n_frames", 2000), self.H, self.W,
+                                                    invalid_frac=d.get("invalid_frac", 0.0), seed=d.get("seed", 1234))
+            self._depth_is_metric = True
+        elif fmt in ("replicaCAD", "replica"):
+            self.scene_dataset = ds.ReplicaDataset(self.ims_file, traj_file=self.traj_file,
+                                                   rgb_transform=ds.bgr_to_rgb, depth_transform=depth_tf,
+                                                   col_ext=".png" if fmt == "replicaCAD" else ".jpg",
+                                                   noisy_depth=self.noisy_depth if fmt == "replicaCAD" else False)
+            self._depth_is_metric = True
+        else:
+            raise NotImplementedError("dataset format %r: only 'synthetic', 'replicaCAD' and 'replica' readers are "
+                                      "provided (dataset IO is outside the hot path)" % fmt)
+        if self.incremental is False:
+            if self.indices is None:
+                n_views = self.config["dataset"].get("n_views", 0)
+                n = len(self.scene_dataset)
+                self.indices = (np.random.choice(np.arange(0, n), size=n_views, replace=False)
+                                if self.config["dataset"].get("random_views") else
+                                np.linspace(0, n, n_views, dtype=int, endpoint=False))
+            self.last_is_keyframe = True
+            self.add_data(self.get_data(self.indices))
+
+    def get_data(self, idxs):
+        """Host frames -> device FrameData (+ per-pixel normals when the normal loss is on)."""
+        out = FrameData()
+        for idx in idxs:
+            s = self.scene_dataset[idx]
+            im_np, depth_np, T_np = s["image"][None, ...], s["depth"][None, ...], s["T"][None, ...]
+            depth = torch.from_numpy(np.ascontiguousarray(depth_np)).float().pin_memory().to(self.device, non_blocking=True)
+            T = torch.from_numpy(np.ascontiguousarray(T_np)).float().pin_memory().to(self.device, non_blocking=True)
+            im = torch.from_numpy(np.ascontiguousarray(im_np)).to(self.device).float() / 255.
+            data = FrameData(frame_id=np.array([idx]), im_batch=im, im_batch_np=im_np, depth_batch=depth,
+                             depth_batch_np=depth_np, T_WC_batch=T, T_WC_batch_np=T_np)
+            if self.do_normal:
+                pc = transform.pointcloud_from_depth_torch(depth[0], self.fx, self.fy, self.cx, self.cy)
+                data.normal_batch = transform.estimate_pointcloud_normals(pc)[None, :]
+            out.add_frame_data(data, replace=False)
+        return out
+
+    def add_data(self, data, replace=False):
+        replace = self.last_is_keyframe is False      # a non-keyframe is overwritten by the next frame
+        self.frames.add_frame_data(data, replace)
+        if self.last_is_keyframe:
+            print("New keyframe. KF ids:", self.frames.frame_id[:-1])
+
+    def add_frame(self, frame_data):
+        if self.last_is_keyframe:
+            self.frozen_sdf_map = copy.deepcopy(self.sdf_map)
+        self.add_data(frame_data)
+        self.steps_since_frame = 0
+        self.last_is_keyframe = False
+        self.optim_frames = self.iters_per_frame
+        self.noise_std = self.noise_frame
+
+    def clear_keyframes(self):
+        self.frames = FrameData()
+        self.gt_depth_vis = self.gt_im_vis = None
+
+    # ---- keyframe logic (trainer.py:586-674) ------------------------------------------------
+    def is_keyframe(self, T_WC, depth_gt):
+        pts = self.sample_points(depth_gt, T_WC, n_rays=self.n_rays_is_kf, dist_behind_surf=0.8)
+        with torch.no_grad():
+            sdf = self.frozen_sdf_map(pts["pc"], noise_std=self.noise_std)
+        z, order = pts["z_vals"].sort(dim=-1)
+        sdf = torch.gather(sdf, 1, order)
+        view_depth = render.sdf_render_depth(z, sdf)
+        err = torch.abs(view_depth - pts["depth_sample"]) / pts["depth_sample"]
+        prop = (err < self.kf_dist_th).float().mean().item()
+        is_kf = prop < self.kf_pixel_ratio
+        print("Proportion of loss below threshold", prop, "for KF should be less than", self.kf_pixel_ratio,
+              " ---> is keyframe:", is_kf)
+        return is_kf
+
+    def check_keyframe_latest(self):
+        if self.last_is_keyframe:
+            return True
+        T_WC = self.frames.T_WC_batch[-1].unsqueeze(0)
+        depth_gt = self.frames.depth_batch[-1].unsqueeze(0)
+        self.last_is_keyframe = self.is_keyframe(T_WC, depth_gt)
+        if self.tot_step_time - self.frames.frame_id[-2] / 30. > 5. and not self.live:
+            print("More than 5 seconds since last kf, so add new")
+            self.last_is_keyframe = True
+        if self.last_is_keyframe:
+            self.optim_frames = self.iters_per_kf
+            self.noise_std = self.noise_kf
+            return False
+        return True
+
+    def select_keyframes(self):
+        """Latest two keyframes + (window_size-2) drawn without replacement with p ~ frame loss."""
+        n = len(self.frames)
+        limit = n - 2
+        w = self.frames.frame_avg_losses[:-2]
+        if self.rng_mode == "fast":
+            pick = torch.multinomial(w / w.sum(), self.window_size - 2, replacement=False)
+            last = torch.tensor([n - 2, n - 1], device=pick.device)
+            return torch.cat([pick, last])
+        p = (w / w.sum()).cpu().numpy()
+        rand_ints = np.random.choice(np.arange(0, limit), size=self.window_size - 2, replace=False, p=p)
+        return [*rand_ints, n - 2, n - 1]
+
+    # ---- sampling (trainer.py:683-766) -------------------------------------------------------
+    def _lin(self, n):
+        if n not in self._lin_cache:
+            self._lin_cache[n] = torch.linspace(0, 1, n + 1).to(self.device)
+        return self._lin_cache[n]
+
+    def sample_points(self, depth_batch, T_WC_batch, norm_batch=None, active_loss_approx=None, n_rays=None,
+                      dist_behind_surf=None, n_strat_samples=None, n_surf_samples=None, frame_map=None):
+        """Pixels -> valid rays -> depths along rays -> 3-D points.  `frame_map` (window slot -> keyframe
+        row) lets the kernels read the full keyframe buffer instead of a gathered depth_batch[idxs] copy."""
+        if active_loss_approx is not None:
+            raise Exception('Active sampling not currently supported.')
+        n_rays = self.n_rays if n_rays is None else n_rays
+        dist_behind_surf = self.dist_behind_surf if dist_behind_surf is None else dist_behind_surf
+        n_strat = self.n_strat_samples if n_strat_samples is None else n_strat_samples
+        n_surf = self.n_surf_samples if n_surf_samples is None else n_surf_samples
+        eng = self.sdf_map.engine()
+        dev = self.device
+        n_frames = depth_batch.shape[0] if frame_map is None else len(frame_map)
+        rd = self.rng_device or dev
+        ib, ih, iw = sample.sample_pixels(n_rays, n_frames, self.H, self.W, device=rd)
+        ib, ih, iw = ib.to(dev), ih.to(dev), iw.to(dev)
+        fmap = None if frame_map is None else torch.as_tensor(frame_map, device=dev, dtype=torch.int64)
+        depth_s, norm_s, valid = eng.gather_rays(depth_batch, norm_batch, ib, ih, iw, self.cam, frame_map=fmap,
+                                                 normals_use_frame_map=self.fix_normal_window)
+        ray_valid = None
+        if self.rng_mode == "reference":
+            keep = valid.bool()                   # data-dependent compaction (host sync, as the reference)
+            depth_s, ib, ih, iw = depth_s[keep], ib[keep], ih[keep], iw[keep]
+            norm_s = norm_s[keep] if norm_s is not None else None
+        else:
+            ray_valid = valid
+        R = depth_s.shape[0]
+        u = torch.rand(R, n_strat, device=rd).to(dev)
+        if self.rng_mode == "reference":
+            near = torch.normal(torch.zeros(R, max(n_surf - 1, 0)), 0.1).to(dev)     # CPU RNG (quirk Q6)
+        else:
+            near = torch.randn(R, max(n_surf - 1, 0), device=dev) * 0.1
+        pc, z_vals, dirs_C_s, T_s = eng.sample_rays(T_WC_batch, ib, ih, iw, depth_s, u, near, self._lin(n_strat),
+                                                    n_strat, n_surf, self.cam, self.min_depth, dist_behind_surf,
+                                                    frame_map=fmap)
+        return {"depth_batch": depth_batch, "pc": pc, "z_vals": z_vals, "indices_b": ib, "indices_h": ih,
+                "indices_w": iw, "dirs_C_sample": dirs_C_s, "depth_sample": depth_s, "T_WC_sample": T_s,
+                "norm_sample": norm_s, "binary_masks": None, "ray_valid": ray_valid, "n_frames": n_frames}
+
+    # ---- fused forward / loss / backward (trainer.py:768-868 + 981) --------------------------
+    def sdf_eval_and_loss(self, sample_pts, do_avg_loss=True):
+        """K4 (+K5).  Returns (total_loss, losses, loss_approx, frame_avg_loss) like the reference;
+        the parameter gradient of total_loss is left in the engine's gradient buffer (the fused
+        kernel already did the double back-prop), so no .backward() follows."""
+        if self.bounds_method != "ray":
+            raise NotImplementedError("bounds_method %r: only 'ray' is fused ('pc' is a next-row item, 'normal' "
+                                      "raises in the reference itself)" % self.bounds_method)
+        eng = self.sdf_map.engine()
+        pc = sample_pts["pc"]
+        R, S = pc.shape[0], pc.shape[1]
+        ray_valid = sample_pts.get("ray_valid")
+        noise = None
+        if self.noise_std is not None:
+            noise = torch.randn(R, S, device=self.rng_device or self.device).to(self.device)
+        inv_dev = None
+        if ray_valid is None:
+            inv_count = 1.0 / max(R * S, 1)
+        else:
+            inv_count = 0.0
+            cnt = ray_valid.sum().float() * S
+            inv_dev = (1.0 / cnt.clamp_min(1.0)).reshape(1)
+        lc = make_loss_cfg(self.trunc_weight, self.trunc_distance, self.eik_weight, self.eik_apply_dist,
+                           self.grad_weight, self.orien_loss, self.loss_type, self.noise_std or 0.0, inv_count,
+                           inv_count_dev=inv_dev)
+        self._loss_sums.zero_()
+        eng.zero_grad()
+        sdf, _, loss_mat, sums = eng.train_fwd_bwd(pc, sample_pts["z_vals"], sample_pts["depth_sample"],
+                                                   sample_pts["dirs_C_sample"], sample_pts["T_WC_sample"],
+                                                   sample_pts["norm_sample"] if self.do_normal else None, noise, lc,
+                                                   ray_valid=ray_valid, want_grad=False, loss_sums=self._loss_sums)
+        means = sums * (inv_dev if inv_dev is not None else inv_count)
+        if self.rng_mode == "reference":
+            host = means.tolist()                                  # the reference's 3 .item() syncs, in one
+            losses = {"sdf_loss": host[0]}
+            if self.grad_weight != 0:
+                losses["grad_loss"] = host[1]
+            if self.eik_weight != 0:
+                losses["eikonal_loss"] = host[2]
+        else:
+            losses = {"sdf_loss": means[0]}
+            if self.grad_weight != 0:
+                losses["grad_loss"] = means[1]
+            if self.eik_weight != 0:
+                losses["eikonal_loss"] = means[2]
+        total_loss = means[3]
+        losses["total_loss"] = total_loss
+        self.last_sdf, self.last_loss_mat = sdf, loss_mat
+        loss_approx = frame_avg_loss = None
+        if do_avg_loss:
+            loss_approx, frame_avg_loss = eng.frame_bins(loss_mat, sample_pts["indices_b"], sample_pts["indices_h"],
+                                                         sample_pts["indices_w"], sample_pts["n_frames"], self.H,
+                                                         self.W, self.loss_approx_factor, ray_valid=ray_valid)
+        return total_loss, losses, loss_approx, frame_avg_loss
+
+    # ---- one optimisation step (trainer.py:951-1016) -----------------------------------------
+    def step(self, sync=True):
+        if sync:
+            start, end = start_timing()
+        depth_batch = self.frames.depth_batch
+        T_WC_batch = self.frames.T_WC_batch
+        norm_batch = self.frames.normal_batch if self.do_normal else None
+        if len(self.frames) > self.window_size and self.incremental:
+            idxs = self.select_keyframes()
+        else:
+            idxs = np.arange(T_WC_batch.shape[0])
+        self.active_idxs = idxs
+        idx_t = torch.as_tensor(idxs, device=self.device, dtype=torch.int64)
+        sample_pts = self.sample_points(depth_batch, T_WC_batch, norm_batch=norm_batch, frame_map=idx_t)
+        self.active_pixels = {k: sample_pts[k] for k in ("indices_b", "indices_h", "indices_w")}
+        total_loss, losses, active_loss_approx, frame_avg_loss = self.sdf_eval_and_loss(sample_pts, do_avg_loss=True)
+        self.frames.frame_avg_losses[idx_t] = frame_avg_loss
+        scale = 1.0
+        if self.dist_world > 1:                                   # C1: the only collective
+            torch.distributed.all_reduce(self.sdf_map.engine().grad_buffer())
+            scale = 1.0 / self.dist_world
+        self.optimiser.step(grad_scale=scale)
+        step_time = end_timing(start, end) if sync else 0.0
+        self.tot_step_time += (1 / self.frac_time_perception) * (step_time / 1000.)
+        self.steps_since_frame += 1
+        return losses, step_time
+
+    def get_sdf_grid_pc(self, *a, **k):
+        raise NotImplementedError("grid / mesh extraction is outside the hot path")

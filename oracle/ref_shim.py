@@ -75,6 +75,13 @@ def load():
     saved = {k: v for k, v in sys.modules.items() if k == "isdf" or k.startswith("isdf.")}
     for k in saved:
         del sys.modules[k]
+    # the repo's own regular `isdf` package would shadow the reference's namespace package
+    # regardless of path order -> hide every path entry that holds it while importing
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hidden = [(i, e) for i, e in enumerate(sys.path)
+              if os.path.isfile(os.path.join(os.path.abspath(e or "."), "isdf", "__init__.py"))]
+    for _, e in hidden:
+        sys.path.remove(e)
     sys.path.insert(0, REFERENCE_ROOT)
     try:
         import warnings
@@ -85,8 +92,11 @@ def load():
             from isdf.datasets import data_util  # noqa
         ref = dict(trainer=trainer, fc_map=fc_map, embedding=embedding, sample=sample,
                    loss=loss, render=render, transform=transform, data_util=data_util)
+        assert trainer.__file__.startswith(REFERENCE_ROOT), trainer.__file__
     finally:
         sys.path.remove(REFERENCE_ROOT)
+        for i, e in hidden:
+            sys.path.insert(min(i, len(sys.path)), e)
         ref_mods = {k: v for k, v in sys.modules.items() if k == "isdf" or k.startswith("isdf.")}
         for k in ref_mods:
             del sys.modules[k]
