@@ -1,0 +1,50 @@
+// Argument block and step program of the tcgen05 chain kernel (tc_chain.cu).
+#pragma once
+#include "tc_common.cuh"
+
+enum { TC_MODE_FWD = 0, TC_MODE_FWD_GRAD = 1, TC_MODE_TRAIN = 2 };
+enum { EPI_RAW = 0, EPI_S1, EPI_S1_LAST, EPI_S2, EPI_S2_END, EPI_S3, EPI_S3_LAST, EPI_S4 };
+
+struct TcStep {
+  int32_t unit;     // weight unit (tc_pack.cu)
+  int32_t orient;   // 0: Y = X W^T (S1, S3)   1: Y = X W (S2, S4)
+  int32_t epi;      // epilogue kind
+  int16_t layer;    // hidden layer whose sigma / bias / side arrays the epilogue uses
+  int16_t aux;      // EPI_RAW: which partial-sum side array (0: S1, 1: S2, 2: S3)
+};
+#define TC_MAX_STEPS (4 * ISDFB_MAX_HIDDEN_LAYERS + 2)
+
+struct TcChainArgs {
+  TcStep steps[TC_MAX_STEPS];
+  int32_t n_steps, mode, L, ic, E, S;
+  int32_t n_tiles;
+  int64_t n_points;          // real points in this chunk
+  int64_t p0;                // global index of the chunk's first point (sample index r*S+j)
+  PEParams pe;
+  isdfb_loss_cfg loss;
+  float scale_output, noise_std;
+  // model
+  const uint8_t* w_img;      // [unit][orient][hi|lo] bf16 K-major images
+  const float* w_packed;     // packed fp32 params (biases, output layer)
+  int64_t lay_b_off[ISDFB_MAX_HIDDEN_LAYERS];
+  int64_t wout_off, bout_off;
+  // inputs / outputs
+  const float* x;            // [n_points,3] (chunk-local)
+  const float* noise;        // [n_points] or null
+  float* sdf_out;            // [n_points]
+  float* g_out;              // [n_points,3] or null
+  const float *z_vals, *depth, *dirs_C, *T_WC, *normals;   // GLOBAL ray arrays (indexed via p0)
+  const uint8_t* ray_valid;
+  float* loss_mat;           // GLOBAL [R*S]
+  float* loss_sums;          // [4]
+  float* g_packed;           // packed gradient (d b_out is accumulated by the chain kernel)
+  // per-tile side state
+  float* aux;                // fp32 arrays [arr][tile][256*128], aux layout
+  size_t aux_stride;         // floats between arrays
+  uint8_t *dwl_hi, *dwl_lo;  // bf16 arrays [arr][tile][64 KB], dW layout
+  size_t dwl_stride;         // bytes between arrays
+  int32_t arr_sig, arr_zb2, arr_part, arr_e32, arr_hlast;   // aux array indices
+  int32_t arr_yh, arr_ya, arr_xd, arr_xz, arr_v;            // dW-layout array indices
+};
+
+int tc_chain_launch(isdfb_ctx* ctx, const TcChainArgs& args, int passes, int grid, cudaStream_t st);

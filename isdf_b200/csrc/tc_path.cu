@@ -1,7 +1,180 @@
-// placeholder until the tcgen05 path lands (replaced in the next milestone)
-#include "common.cuh"
-int tc_create(isdfb_ctx* ctx) { ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "tensor-core path not built yet"); }
-void tc_destroy(isdfb_ctx*) {}
-int tc_repack(isdfb_ctx*, cudaStream_t) { return ISDFB_OK; }
-int tc_forward(isdfb_ctx* ctx, const float*, const float*, float, int64_t, float*, float*, cudaStream_t) { ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "tensor-core path not built yet"); }
-int tc_train(isdfb_ctx* ctx, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const uint8_t*, int64_t, int32_t, const isdfb_loss_cfg*, float*, float*, float*, float*, cudaStream_t) { ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "tensor-core path not built yet"); }
+// Host orchestration of the tensor-core path: state, step programs, weight-gradient jobs, launches.
+#include "tc_path.cuh"
+#include <new>
+
+static void add_step(TcChainArgs& a, int unit, int orient, int epi, int layer, int aux = 0) {
+  TcStep& s = a.steps[a.n_steps++];
+  s.unit = unit; s.orient = orient; s.epi = epi; s.layer = (int16_t)layer; s.aux = (int16_t)aux;
+}
+
+static void build_program(const ModelLayout& lay, int mode, TcChainArgs& a) {
+  const int L = lay.L, ic = lay.block + 1, UE = L;   // unit index of the concat layer's embedding part
+  a.n_steps = 0;
+  add_step(a, UE, 0, EPI_RAW, 0, 0);
+  for (int l = 0; l < L; ++l) add_step(a, l, 0, l == L - 1 ? EPI_S1_LAST : EPI_S1, l);
+  if (mode == TC_MODE_FWD) return;
+  for (int l = L - 1; l >= 1; --l) {
+    if (l == ic) add_step(a, UE, 1, EPI_RAW, l, 1);
+    add_step(a, l, 1, EPI_S2, l - 1);
+  }
+  add_step(a, 0, 1, EPI_S2_END, 0);
+  if (mode == TC_MODE_FWD_GRAD) return;
+  add_step(a, UE, 0, EPI_RAW, 0, 2);
+  for (int l = 0; l < L; ++l) add_step(a, l, 0, l == L - 1 ? EPI_S3_LAST : EPI_S3, l);
+  for (int l = L - 1; l >= 1; --l) add_step(a, l, 1, EPI_S4, l - 1);
+}
+
+void tc_destroy(isdfb_ctx* ctx) {
+  TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
+  if (!tc) return;
+  if (tc->w_img) cudaFree(tc->w_img);
+  if (tc->aux) cudaFree(tc->aux);
+  if (tc->dwl_hi) cudaFree(tc->dwl_hi);
+  if (tc->dwl_lo) cudaFree(tc->dwl_lo);
+  delete tc;
+  ctx->tc = nullptr;
+}
+
+int tc_create(isdfb_ctx* ctx) {
+  const ModelLayout& lay = ctx->lay;
+  if (lay.H != TC_H || lay.Ep != TC_H)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG,
+               "tensor-core path supports hidden=256 and embedding <= 256 (n_freqs <= 6); got hidden=%d E=%d. "
+               "Use precision fp32 for other shapes.", lay.H, lay.E);
+  TcState* tc = new (std::nothrow) TcState();
+  if (!tc) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "out of host memory");
+  memset(tc, 0, sizeof(*tc));
+  ctx->tc = tc;
+  const int L = lay.L, ic = lay.block + 1;
+  ISDFB_CUDA_OK(ctx, cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  tc->n_units = L + 1;
+  for (int l = 0; l < L; ++l) { tc->units.u[l].w_off = lay.layer[l].w_off; tc->units.u[l].ld = lay.layer[l].k0; }
+  tc->units.u[L].w_off = lay.layer[ic].we_off;
+  tc->units.u[L].ld = lay.Ep;
+  tc->tiles_cap = ctx->cap / TC_TILE;
+  tc->n_aux = 2 * L + 5;
+  tc->n_dwl = 4 * L + 1;
+  tc->aux_stride = (size_t)tc->tiles_cap * TC_TILE_FLOATS;
+  tc->dwl_stride = (size_t)tc->tiles_cap * TC_DWL_TILE_BYTES;
+  ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->w_img, (size_t)tc->n_units * 4 * TC_IMG_BYTES));
+  ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->aux, tc->aux_stride * tc->n_aux * sizeof(float)));
+  ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dwl_hi, tc->dwl_stride * tc->n_dwl));
+  if (ctx->cfg.precision == ISDFB_PREC_BF16X3) ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dwl_lo, tc->dwl_stride * tc->n_dwl));
+
+  for (int mode = 0; mode < 3; ++mode) {
+    TcChainArgs& a = tc->proto[mode];
+    memset(&a, 0, sizeof(a));
+    build_program(lay, mode, a);
+    a.mode = mode; a.L = L; a.ic = ic; a.E = lay.E;
+    a.pe = ctx->pe;
+    a.scale_output = ctx->cfg.scale_output;
+    a.w_img = tc->w_img;
+    a.w_packed = ctx->w_packed;
+    a.g_packed = ctx->g_packed;
+    for (int l = 0; l < L; ++l) a.lay_b_off[l] = lay.layer[l].b_off;
+    a.wout_off = lay.wout_off; a.bout_off = lay.bout_off;
+    a.aux = tc->aux; a.aux_stride = tc->aux_stride;
+    a.dwl_hi = tc->dwl_hi; a.dwl_lo = tc->dwl_lo; a.dwl_stride = tc->dwl_stride;
+    a.arr_sig = 0; a.arr_zb2 = L; a.arr_part = 2 * L; a.arr_e32 = 2 * L + 3; a.arr_hlast = 2 * L + 4;
+    a.arr_yh = 0; a.arr_ya = L; a.arr_xd = 2 * L; a.arr_xz = 3 * L; a.arr_v = 4 * L;
+  }
+  // weight-gradient jobs
+  TcDwArgs& d = tc->dw;
+  memset(&d, 0, sizeof(d));
+  const TcChainArgs& a = tc->proto[TC_MODE_TRAIN];
+  for (int u = 0; u <= L; ++u) {
+    for (int half = 0; half < 2; ++half) {
+      TcDwJob& j = d.jobs[d.n_jobs++];
+      j.half = half;
+      j.ld = TC_H;
+      if (u < L) {
+        j.g_off = lay.layer[u].w_off;
+        j.db_off = lay.layer[u].b_off;
+        j.pair[0] = {a.arr_xd + u, a.arr_ya + u, 0};
+        j.pair[1] = {a.arr_xz + u, a.arr_yh + u, 1};
+        j.n_pairs = 2;
+        if (u == L - 1) { j.pair[2] = {a.arr_v, -1, 2}; j.n_pairs = 3; }
+      } else {
+        j.g_off = lay.layer[ic].we_off;
+        j.db_off = -1;
+        j.pair[0] = {a.arr_xd + ic, a.arr_ya + 0, 0};
+        j.pair[1] = {a.arr_xz + ic, a.arr_yh + 0, 0};
+        j.n_pairs = 2;
+      }
+    }
+  }
+  d.dwl_hi = tc->dwl_hi; d.dwl_lo = tc->dwl_lo; d.dwl_stride = tc->dwl_stride;
+  d.g_packed = ctx->g_packed;
+  d.wout_off = lay.wout_off;
+  d.scale_output = ctx->cfg.scale_output;
+  return ISDFB_OK;
+}
+
+static inline int passes_of(const isdfb_ctx* ctx) { return ctx->cfg.precision == ISDFB_PREC_BF16X3 ? 3 : 1; }
+
+int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n, float* sdf,
+               float* grad, cudaStream_t st) {
+  TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
+  for (int64_t p0 = 0; p0 < n; p0 += ctx->cap) {
+    const int64_t nc = (n - p0 < ctx->cap) ? (n - p0) : ctx->cap;
+    TcChainArgs a = tc->proto[grad ? TC_MODE_FWD_GRAD : TC_MODE_FWD];
+    a.n_points = nc;
+    a.n_tiles = (int)((nc + TC_TILE - 1) / TC_TILE);
+    a.p0 = p0;
+    a.x = x + p0 * 3;
+    a.noise = noise ? noise + p0 : nullptr;
+    a.noise_std = noise_std;
+    a.sdf_out = sdf + p0;
+    a.g_out = grad ? grad + p0 * 3 : nullptr;
+    const int grid = a.n_tiles < tc->num_sms ? a.n_tiles : tc->num_sms;
+    int rc = tc_chain_launch(ctx, a, passes_of(ctx), grid, st);
+    if (rc) return rc;
+  }
+  return ISDFB_OK;
+}
+
+int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample, const float* dirs_C,
+             const float* T_WC_sample, const float* norm_sample, const float* noise, const uint8_t* ray_valid,
+             int64_t n_rays, int32_t S, const isdfb_loss_cfg* loss, float* sdf, float* grad, float* loss_mat,
+             float* loss_sums, cudaStream_t st) {
+  TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
+  const int64_t n = n_rays * S;
+  for (int64_t p0 = 0; p0 < n; p0 += ctx->cap) {
+    const int64_t nc = (n - p0 < ctx->cap) ? (n - p0) : ctx->cap;
+    TcChainArgs a = tc->proto[TC_MODE_TRAIN];
+    a.n_points = nc;
+    a.n_tiles = (int)((nc + TC_TILE - 1) / TC_TILE);
+    a.p0 = p0;
+    a.S = S;
+    a.loss = *loss;
+    a.x = pc + p0 * 3;
+    a.noise = noise ? noise + p0 : nullptr;
+    a.noise_std = loss->noise_std;
+    a.sdf_out = sdf + p0;
+    a.g_out = grad ? grad + p0 * 3 : nullptr;
+    a.z_vals = z_vals; a.depth = depth_sample; a.dirs_C = dirs_C; a.T_WC = T_WC_sample; a.normals = norm_sample;
+    a.ray_valid = ray_valid;
+    a.loss_mat = loss_mat;
+    a.loss_sums = loss_sums;
+    const int grid = a.n_tiles < tc->num_sms ? a.n_tiles : tc->num_sms;
+    int rc = tc_chain_launch(ctx, a, passes_of(ctx), grid, st);
+    if (rc) return rc;
+    TcDwArgs d = tc->dw;
+    d.n_tiles = a.n_tiles;
+    rc = tc_dw_launch(ctx, d, passes_of(ctx), tc->num_sms, st);
+    if (rc) return rc;
+  }
+  return ISDFB_OK;
+}
+
+extern "C" int isdfb_debug_buffers(isdfb_ctx* ctx, float** aux, int64_t* aux_stride_floats, void** dwl_hi,
+                                   void** dwl_lo, int64_t* dwl_stride_bytes, int32_t* n_aux, int32_t* n_dwl,
+                                   int64_t* tiles_cap) {
+  if (!ctx) return ISDFB_ERR_ARG;
+  TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
+  if (!tc) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "no tensor-core state (fp32 path)");
+  *aux = tc->aux; *aux_stride_floats = (int64_t)tc->aux_stride;
+  *dwl_hi = tc->dwl_hi; *dwl_lo = tc->dwl_lo; *dwl_stride_bytes = (int64_t)tc->dwl_stride;
+  *n_aux = tc->n_aux; *n_dwl = tc->n_dwl; *tiles_cap = tc->tiles_cap;
+  return ISDFB_OK;
+}

@@ -1,0 +1,42 @@
+// Host-side state of the tensor-core path.
+#pragma once
+#include "tc_chain.cuh"
+
+struct TcUnitTable { TcUnit u[TC_MAX_UNITS]; };
+
+// weight-gradient job: one 128-row half of one weight unit; up to three (X, Y) operand pairs
+struct TcDwPair { int32_t x_arr, y_arr, ones; };      // y_arr < 0: no main product; ones: 0 none, 1 -> db, 2 -> d w_out
+struct TcDwJob {
+  int32_t half;            // which 128 output rows
+  int32_t n_pairs;
+  TcDwPair pair[3];
+  int64_t g_off;           // packed-gradient offset of the unit's [256][ld] block
+  int32_t ld;
+  int64_t db_off;          // packed-gradient offset of the bias (or -1)
+};
+#define TC_MAX_JOBS (2 * TC_MAX_UNITS)
+
+struct TcDwArgs {
+  TcDwJob jobs[TC_MAX_JOBS];
+  int32_t n_jobs, n_tiles;
+  const uint8_t *dwl_hi, *dwl_lo;
+  size_t dwl_stride;
+  float* g_packed;
+  int64_t wout_off;
+  float scale_output;
+};
+
+struct TcState {
+  int n_units, num_sms;
+  TcUnitTable units;
+  uint8_t* w_img;          // [unit][orient][hi|lo] x 128 KB
+  float* aux;
+  uint8_t *dwl_hi, *dwl_lo;
+  int64_t tiles_cap;
+  size_t aux_stride, dwl_stride;
+  int n_aux, n_dwl;
+  TcChainArgs proto[3];    // per mode: steps and array indices filled in at create
+  TcDwArgs dw;
+};
+
+int tc_dw_launch(isdfb_ctx* ctx, const TcDwArgs& args, int passes, int grid, cudaStream_t st);

@@ -263,3 +263,35 @@ def make_camera(fx, fy, cx, cy, H, W):
     cam = _lib.Camera()
     cam.fx, cam.fy, cam.cx, cam.cy, cam.H, cam.W = float(fx), float(fy), float(cx), float(cy), int(H), int(W)
     return cam
+
+
+def debug_state(engine):
+    """Test helper: decode the tensor-core path's per-tile side arrays into [points, 256] tensors.
+    Returns (aux(arr) -> fp32 [tiles*128, 256], dwl(arr) -> fp32 [tiles*128, 256] (hi + lo))."""
+    aux, dhi, dlo = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    a_st, d_st, tiles = C.c_int64(), C.c_int64(), C.c_int64()
+    n_aux, n_dwl = C.c_int32(), C.c_int32()
+    engine._ck(engine.lib.isdfb_debug_buffers(engine._ctx, C.byref(aux), C.byref(a_st), C.byref(dhi), C.byref(dlo),
+                                              C.byref(d_st), C.byref(n_aux), C.byref(n_dwl), C.byref(tiles)))
+    T = tiles.value
+    aux_t = _DevView(aux.value, a_st.value * n_aux.value, engine.device).tensor.view(n_aux.value, T, 64, 128, 4)
+
+    def raw16(ptr):
+        v = _DevView(ptr, d_st.value * n_dwl.value // 4, engine.device).tensor      # fp32 view of the bytes
+        return v.view(torch.int16).view(n_dwl.value, T, 8, 32, 16, 8)
+
+    hi = raw16(dhi.value)
+    lo = raw16(dlo.value) if dlo.value else None
+
+    def get_aux(arr, n_tiles):
+        return aux_t[arr, :n_tiles].permute(0, 2, 1, 3).reshape(n_tiles * 128, 256).clone()
+
+    def get_dwl(arr, n_tiles, part="sum"):
+        def dec(x):
+            return x[arr, :n_tiles].permute(0, 1, 3, 2, 4).reshape(n_tiles * 128, 256).contiguous().view(torch.bfloat16).float()
+        h = dec(hi)
+        if part == "hi" or lo is None:
+            return h
+        return h + dec(lo)
+
+    return get_aux, get_dwl
