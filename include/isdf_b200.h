@@ -164,13 +164,22 @@ int isdfb_adamw(isdfb_ctx* ctx, float* params_flat, float* m, float* v, int64_t 
 /* ctx-internal gradient buffer (fp32, padded internal layout) for the NCCL all-reduce.     */
 int isdfb_grad_buffer(isdfb_ctx* ctx, float** ptr, int64_t* n_floats);
 
+/* ---- kernel timing (bench.py roofline) ---------------------------------------------------
+ * When enabled, the tensor-core path brackets its two kernels (the fused PE+MLP chain kernel and
+ * the weight-gradient kernel) with CUDA events on the launching stream.  isdfb_profile_read
+ * synchronises on the last event, returns the summed durations / launch counts since the last
+ * read, and clears them.  Off by default (no events are recorded in normal operation).        */
+int isdfb_profile_enable(isdfb_ctx* ctx, int32_t enable);
+int isdfb_profile_read(isdfb_ctx* ctx, double* chain_ms, double* dw_ms, int64_t* n_chain, int64_t* n_dw);
+
 /* ---- debug hook (tests only): raw per-tile side state of the tensor-core path -------------
  * aux: fp32 arrays [n_aux][tiles_cap][256*128] in the aux layout, dwl_hi/lo: bf16 arrays
- * [n_dwl][tiles_cap][64 KB] in the dW layout (isdf_b200/csrc/tc_common.cuh).  Returns
+ * [n_dwl][tiles_cap][64 KB] in the dW layout, sig16: unorm16 sigma [L][tiles_cap][64 KB]
+ * (isdf_b200/csrc/tc_common.cuh).  Returns
  * ISDFB_ERR_STATE for the fp32 path.                                                        */
 int isdfb_debug_buffers(isdfb_ctx* ctx, float** aux, int64_t* aux_stride_floats, void** dwl_hi,
                         void** dwl_lo, int64_t* dwl_stride_bytes, int32_t* n_aux, int32_t* n_dwl,
-                        int64_t* tiles_cap);
+                        int64_t* tiles_cap, void** sig16);
 
 #ifdef __cplusplus
 }

@@ -58,8 +58,10 @@ SIGNATURES = {
     "isdfb_frame_bins": (C.c_int, [P, P, P, P, P, P, I64, I32, I32, I32, I32, I32, P, P, P]),
     "isdfb_adamw": (C.c_int, [P, P, P, P, I64, F, F, F, F, F, F, P]),
     "isdfb_grad_buffer": (C.c_int, [P, C.POINTER(P), C.POINTER(I64)]),
+    "isdfb_profile_enable": (C.c_int, [P, I32]),
+    "isdfb_profile_read": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(I64)]),
     "isdfb_debug_buffers": (C.c_int, [P, C.POINTER(P), C.POINTER(I64), C.POINTER(P), C.POINTER(P), C.POINTER(I64),
-                                      C.POINTER(I32), C.POINTER(I32), C.POINTER(I64)]),
+                                      C.POINTER(I32), C.POINTER(I32), C.POINTER(I64), C.POINTER(P)]),
 }
 
 _lib = None

@@ -18,6 +18,7 @@ struct TcChainArgs {
   TcStep steps[TC_MAX_STEPS];
   int32_t n_steps, mode, L, ic, E, S;
   int32_t n_tiles;
+  int32_t prefetch;          // 1: bulk-prefetch the next step's side arrays into L2 (producer warp)
   int64_t n_points;          // real points in this chunk
   int64_t p0;                // global index of the chunk's first point (sample index r*S+j)
   PEParams pe;
@@ -42,9 +43,12 @@ struct TcChainArgs {
   float* aux;                // fp32 arrays [arr][tile][256*128], aux layout
   size_t aux_stride;         // floats between arrays
   uint8_t *dwl_hi, *dwl_lo;  // bf16 arrays [arr][tile][64 KB], dW layout
+  uint8_t* sig16;            // sigma_l as unorm16, [layer][tile][64 KB], K-major image layout [f/8][p][8]
+  size_t sig16_stride;       // bytes between layers
   size_t dwl_stride;         // bytes between arrays
-  int32_t arr_sig, arr_zb2, arr_part, arr_e32, arr_hlast;   // aux array indices
+  int32_t arr_zb2, arr_part, arr_e32, arr_hlast;            // aux array indices
   int32_t arr_yh, arr_ya, arr_xd, arr_xz, arr_v;            // dW-layout array indices
+  uint8_t feat_d[TC_H], feat_f[TC_H];                       // PE column -> (direction, octave)
 };
 
 int tc_chain_launch(isdfb_ctx* ctx, const TcChainArgs& args, int passes, int grid, cudaStream_t st);

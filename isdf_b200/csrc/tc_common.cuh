@@ -75,6 +75,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// bring a contiguous global range into L2 ahead of use (no registers, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- TMEM ---------------------------------------------------------------------------------------
@@ -114,6 +118,59 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// sigma in [0,1] as unorm16 (abs error 7.6e-6; 0 and 1 exact): 8 values <-> 16 B
+__device__ __forceinline__ uint4 pack_unorm16x8(const float* s) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t a = __float2uint_rn(s[2 * i] * 65535.f), b = __float2uint_rn(s[2 * i + 1] * 65535.f);
+    w[i] = a | (b << 16);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void unpack_unorm16x8(const uint4& v, float* s) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s[2 * i] = (float)(w[i] & 0xFFFFu) * (1.f / 65535.f);
+    s[2 * i + 1] = (float)(w[i] >> 16) * (1.f / 65535.f);
+  }
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// softplus(beta=100, threshold=20) and sigmoid(100 z) on the SFU (ex2 / lg2 / rcp approximations:
+// relative error ~2^-22, far below the bf16x3 product error)
+__device__ __forceinline__ void softplus100_fast(float z, float& h, float& sig) {
+  const float bz = 100.f * z;
+  const float t = __expf(fminf(bz, 30.f));
+  const float u = 1.f + t;
+  const bool lin = bz > 20.f;
+  sig = lin ? 1.f : __fdividef(t, u);
+  h = lin ? z : __logf(u) * 0.01f;
 }
 
 // ---- descriptors --------------------------------------------------------------------------------

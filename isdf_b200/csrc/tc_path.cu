@@ -1,6 +1,7 @@
 // Host orchestration of the tensor-core path: state, step programs, weight-gradient jobs, launches.
 #include "tc_path.cuh"
 #include <new>
+#include <stdlib.h>
 
 static void add_step(TcChainArgs& a, int unit, int orient, int epi, int layer, int aux = 0) {
   TcStep& s = a.steps[a.n_steps++];
@@ -31,6 +32,10 @@ void tc_destroy(isdfb_ctx* ctx) {
   if (tc->aux) cudaFree(tc->aux);
   if (tc->dwl_hi) cudaFree(tc->dwl_hi);
   if (tc->dwl_lo) cudaFree(tc->dwl_lo);
+  if (tc->sig16) cudaFree(tc->sig16);
+  for (int i = 0; i < TC_PROF_MAX; ++i)
+    for (int k = 0; k < 3; ++k)
+      if (tc->ev[i][k]) cudaEventDestroy(tc->ev[i][k]);
   delete tc;
   ctx->tc = nullptr;
 }
@@ -52,13 +57,14 @@ int tc_create(isdfb_ctx* ctx) {
   tc->units.u[L].w_off = lay.layer[ic].we_off;
   tc->units.u[L].ld = lay.Ep;
   tc->tiles_cap = ctx->cap / TC_TILE;
-  tc->n_aux = 2 * L + 5;
+  tc->n_aux = L + 5;
   tc->n_dwl = 4 * L + 1;
   tc->aux_stride = (size_t)tc->tiles_cap * TC_TILE_FLOATS;
   tc->dwl_stride = (size_t)tc->tiles_cap * TC_DWL_TILE_BYTES;
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->w_img, (size_t)tc->n_units * 4 * TC_IMG_BYTES));
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->aux, tc->aux_stride * tc->n_aux * sizeof(float)));
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dwl_hi, tc->dwl_stride * tc->n_dwl));
+  ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->sig16, tc->dwl_stride * L));
   if (ctx->cfg.precision == ISDFB_PREC_BF16X3) ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dwl_lo, tc->dwl_stride * tc->n_dwl));
 
   for (int mode = 0; mode < 3; ++mode) {
@@ -66,6 +72,7 @@ int tc_create(isdfb_ctx* ctx) {
     memset(&a, 0, sizeof(a));
     build_program(lay, mode, a);
     a.mode = mode; a.L = L; a.ic = ic; a.E = lay.E;
+    a.prefetch = getenv("ISDFB_NO_PREFETCH") ? 0 : 1;
     a.pe = ctx->pe;
     a.scale_output = ctx->cfg.scale_output;
     a.w_img = tc->w_img;
@@ -75,7 +82,16 @@ int tc_create(isdfb_ctx* ctx) {
     a.wout_off = lay.wout_off; a.bout_off = lay.bout_off;
     a.aux = tc->aux; a.aux_stride = tc->aux_stride;
     a.dwl_hi = tc->dwl_hi; a.dwl_lo = tc->dwl_lo; a.dwl_stride = tc->dwl_stride;
-    a.arr_sig = 0; a.arr_zb2 = L; a.arr_part = 2 * L; a.arr_e32 = 2 * L + 3; a.arr_hlast = 2 * L + 4;
+    a.sig16 = tc->sig16; a.sig16_stride = tc->dwl_stride;
+    a.arr_zb2 = 0; a.arr_part = L; a.arr_e32 = L + 3; a.arr_hlast = L + 4;
+    for (int k = 0; k < TC_H; ++k) {
+      int q = k - 3;
+      const int half = ISDFB_NDIRS * lay.n_freqs;
+      if (k < 3 || k >= lay.E) { a.feat_d[k] = 0; a.feat_f[k] = 0; continue; }
+      if (q >= half) q -= half;
+      a.feat_d[k] = (uint8_t)(q / lay.n_freqs);
+      a.feat_f[k] = (uint8_t)(q % lay.n_freqs);
+    }
     a.arr_yh = 0; a.arr_ya = L; a.arr_xd = 2 * L; a.arr_xz = 3 * L; a.arr_v = 4 * L;
   }
   // weight-gradient jobs
@@ -110,6 +126,21 @@ int tc_create(isdfb_ctx* ctx) {
   return ISDFB_OK;
 }
 
+static int prof_begin(TcState* tc, cudaStream_t st) {
+  if (!tc->profiling || tc->n_ev >= TC_PROF_MAX) return -1;
+  const int i = tc->n_ev++;
+  for (int k = 0; k < 3; ++k)
+    if (!tc->ev[i][k]) cudaEventCreate(&tc->ev[i][k]);
+  tc->ev_kind[i] = 0;
+  cudaEventRecord(tc->ev[i][0], st);
+  return i;
+}
+static void prof_mark(TcState* tc, int i, int k, cudaStream_t st) {
+  if (i < 0) return;
+  cudaEventRecord(tc->ev[i][k], st);
+  tc->ev_kind[i] = k;
+}
+
 static inline int passes_of(const isdfb_ctx* ctx) { return ctx->cfg.precision == ISDFB_PREC_BF16X3 ? 3 : 1; }
 
 int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n, float* sdf,
@@ -127,8 +158,10 @@ int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_s
     a.sdf_out = sdf + p0;
     a.g_out = grad ? grad + p0 * 3 : nullptr;
     const int grid = a.n_tiles < tc->num_sms ? a.n_tiles : tc->num_sms;
+    const int pi = prof_begin(tc, st);
     int rc = tc_chain_launch(ctx, a, passes_of(ctx), grid, st);
     if (rc) return rc;
+    prof_mark(tc, pi, 1, st);
   }
   return ISDFB_OK;
 }
@@ -157,24 +190,58 @@ int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* 
     a.loss_mat = loss_mat;
     a.loss_sums = loss_sums;
     const int grid = a.n_tiles < tc->num_sms ? a.n_tiles : tc->num_sms;
+    const int pi = prof_begin(tc, st);
     int rc = tc_chain_launch(ctx, a, passes_of(ctx), grid, st);
     if (rc) return rc;
+    prof_mark(tc, pi, 1, st);
     TcDwArgs d = tc->dw;
     d.n_tiles = a.n_tiles;
     rc = tc_dw_launch(ctx, d, passes_of(ctx), tc->num_sms, st);
     if (rc) return rc;
+    prof_mark(tc, pi, 2, st);
   }
   return ISDFB_OK;
 }
 
 extern "C" int isdfb_debug_buffers(isdfb_ctx* ctx, float** aux, int64_t* aux_stride_floats, void** dwl_hi,
                                    void** dwl_lo, int64_t* dwl_stride_bytes, int32_t* n_aux, int32_t* n_dwl,
-                                   int64_t* tiles_cap) {
+                                   int64_t* tiles_cap, void** sig16) {
   if (!ctx) return ISDFB_ERR_ARG;
   TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
   if (!tc) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "no tensor-core state (fp32 path)");
   *aux = tc->aux; *aux_stride_floats = (int64_t)tc->aux_stride;
   *dwl_hi = tc->dwl_hi; *dwl_lo = tc->dwl_lo; *dwl_stride_bytes = (int64_t)tc->dwl_stride;
-  *n_aux = tc->n_aux; *n_dwl = tc->n_dwl; *tiles_cap = tc->tiles_cap;
+  *n_aux = tc->n_aux; *n_dwl = tc->n_dwl; *tiles_cap = tc->tiles_cap; *sig16 = tc->sig16;
+  return ISDFB_OK;
+}
+
+extern "C" int isdfb_profile_enable(isdfb_ctx* ctx, int32_t enable) {
+  if (!ctx) return ISDFB_ERR_ARG;
+  TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
+  if (!tc) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "kernel timing is available on the tensor-core path only");
+  tc->profiling = enable != 0;
+  tc->n_ev = 0;
+  return ISDFB_OK;
+}
+
+extern "C" int isdfb_profile_read(isdfb_ctx* ctx, double* chain_ms, double* dw_ms, int64_t* n_chain, int64_t* n_dw) {
+  if (!ctx || !chain_ms || !dw_ms || !n_chain || !n_dw) return ISDFB_ERR_ARG;
+  TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
+  if (!tc) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "kernel timing is available on the tensor-core path only");
+  ISDFB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  *chain_ms = *dw_ms = 0.0; *n_chain = *n_dw = 0;
+  for (int i = 0; i < tc->n_ev; ++i) {
+    const int k = tc->ev_kind[i];
+    if (k < 1) continue;
+    float ms = 0.f;
+    ISDFB_CUDA_OK(ctx, cudaEventSynchronize(tc->ev[i][k]));
+    ISDFB_CUDA_OK(ctx, cudaEventElapsedTime(&ms, tc->ev[i][0], tc->ev[i][1]));
+    *chain_ms += ms; ++*n_chain;
+    if (k == 2) {
+      ISDFB_CUDA_OK(ctx, cudaEventElapsedTime(&ms, tc->ev[i][1], tc->ev[i][2]));
+      *dw_ms += ms; ++*n_dw;
+    }
+  }
+  tc->n_ev = 0;
   return ISDFB_OK;
 }

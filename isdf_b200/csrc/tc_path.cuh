@@ -2,6 +2,7 @@
 #pragma once
 #include "tc_chain.cuh"
 
+#define TC_PROF_MAX 512
 struct TcUnitTable { TcUnit u[TC_MAX_UNITS]; };
 
 // weight-gradient job: one 128-row half of one weight unit; up to three (X, Y) operand pairs
@@ -31,12 +32,17 @@ struct TcState {
   TcUnitTable units;
   uint8_t* w_img;          // [unit][orient][hi|lo] x 128 KB
   float* aux;
-  uint8_t *dwl_hi, *dwl_lo;
+  uint8_t *dwl_hi, *dwl_lo, *sig16;
   int64_t tiles_cap;
   size_t aux_stride, dwl_stride;
   int n_aux, n_dwl;
   TcChainArgs proto[3];    // per mode: steps and array indices filled in at create
   TcDwArgs dw;
+  // optional kernel timing
+  bool profiling;
+  cudaEvent_t ev[TC_PROF_MAX][3];   // before chain, after chain, after dW
+  int ev_kind[TC_PROF_MAX];         // 1: chain only, 2: chain + dW
+  int n_ev;
 };
 
 int tc_dw_launch(isdfb_ctx* ctx, const TcDwArgs& args, int passes, int grid, cudaStream_t st);

@@ -230,6 +230,17 @@ class Engine:
                                       self._stream()))
 
 
+    # ---- kernel timing -------------------------------------------------
+    def profile(self, enable):
+        self._ck(self.lib.isdfb_profile_enable(self._ctx, 1 if enable else 0))
+
+    def profile_read(self):
+        c, d = C.c_double(), C.c_double()
+        nc, nd = C.c_int64(), C.c_int64()
+        self._ck(self.lib.isdfb_profile_read(self._ctx, C.byref(c), C.byref(d), C.byref(nc), C.byref(nd)))
+        return dict(chain_ms=c.value, dw_ms=d.value, n_chain=nc.value, n_dw=nd.value)
+
+
 class _DevView:
     """Wrap a raw device pointer as a torch tensor through __cuda_array_interface__."""
 
@@ -267,12 +278,12 @@ def make_camera(fx, fy, cx, cy, H, W):
 
 def debug_state(engine):
     """Test helper: decode the tensor-core path's per-tile side arrays into [points, 256] tensors.
-    Returns (aux(arr) -> fp32 [tiles*128, 256], dwl(arr) -> fp32 [tiles*128, 256] (hi + lo))."""
-    aux, dhi, dlo = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    Returns (aux(arr), dwl(arr) (hi + lo), sig(layer)), each -> fp32 [tiles*128, 256]."""
+    aux, dhi, dlo, sg = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
     a_st, d_st, tiles = C.c_int64(), C.c_int64(), C.c_int64()
     n_aux, n_dwl = C.c_int32(), C.c_int32()
     engine._ck(engine.lib.isdfb_debug_buffers(engine._ctx, C.byref(aux), C.byref(a_st), C.byref(dhi), C.byref(dlo),
-                                              C.byref(d_st), C.byref(n_aux), C.byref(n_dwl), C.byref(tiles)))
+                                              C.byref(d_st), C.byref(n_aux), C.byref(n_dwl), C.byref(tiles), C.byref(sg)))
     T = tiles.value
     aux_t = _DevView(aux.value, a_st.value * n_aux.value, engine.device).tensor.view(n_aux.value, T, 64, 128, 4)
 
@@ -294,4 +305,9 @@ def debug_state(engine):
             return h
         return h + dec(lo)
 
-    return get_aux, get_dwl
+    def get_sig(layer, n_tiles, n_layers):
+        v = _DevView(sg.value, d_st.value * n_layers // 4, engine.device).tensor.view(torch.int16)
+        v = v.view(n_layers, T, 32, 128, 8)[layer, :n_tiles].permute(0, 2, 1, 3).reshape(n_tiles * 128, 256)
+        return (v.to(torch.int32) & 0xFFFF).float() / 65535.0
+
+    return get_aux, get_dwl, get_sig

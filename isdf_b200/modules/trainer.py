@@ -373,6 +373,7 @@ class Trainer:
         n = len(self.frames)
         limit = n - 2
         w = self.frames.frame_avg_losses[:-2]
+        w = w + (w.sum() <= 0)                 # all-zero history -> uniform (the reference would divide 0/0)
         if self.rng_mode == "fast":
             pick = torch.multinomial(w / w.sum(), self.window_size - 2, replacement=False)
             last = torch.tensor([n - 2, n - 1], device=pick.device)

@@ -52,8 +52,8 @@ def main():
     errs = P.compare_train(out, ref)
     print("K4 train:", {k: ("%.3e" % v if not isinstance(v, list) else ["%.2e" % t for t in v]) for k, v in errs.items()})
 
-    get_aux, get_dwl = debug_state(eng)
-    A_SIG, A_ZB2, A_PART, A_E32, A_HL = 0, L, 2 * L, 2 * L + 3, 2 * L + 4
+    get_aux, get_dwl, get_sig = debug_state(eng)
+    A_ZB2, A_PART, A_E32, A_HL = 0, L, L + 3, L + 4
     D_YH, D_YA, D_XD, D_XZ, D_V = 0, L, 2 * L, 3 * L, 4 * L
 
     def show(name, got, want):
@@ -65,7 +65,7 @@ def main():
     show("e32", get_aux(A_E32, nt), refi["e"])
     show("Yh[0]=e", get_dwl(D_YH, nt), refi["e"])
     for l in range(L):
-        show("sig[%d]" % l, get_aux(A_SIG + l, nt), refi["sig"][l])
+        show("sig[%d]" % l, get_sig(l, nt, L), refi["sig"][l])
     for l in range(1, L):
         show("Yh[%d]=h%d" % (l, l - 1), get_dwl(D_YH + l, nt), refi["inps"][l][:, :256])
     show("h_last", get_aux(A_HL, nt), refi["h_last"])
