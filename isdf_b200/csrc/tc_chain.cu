@@ -46,6 +46,215 @@ __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
 
+// ---------------------------------------------------------------------------------------------
+// epilogue building blocks.  Thread (q, jg) handles point p = 32q + lane and, in every 64-column
+// K chunk c, the 16 columns [64c + 16jg, +16) as two 8-column sub-pieces h = 0, 1.
+// ---------------------------------------------------------------------------------------------
+struct EpiT {                       // per-thread / per-tile constants (thread offsets folded in)
+  uint8_t *a_hi, *a_lo;             // smem A images  + p*16 + (2 jg) A_LBO
+  uint8_t *dwl_hi, *dwl_lo;         // dW-layout array 0 + tile + (p>>4) 8192 + (p&15) 16 + (2 jg) 256
+  float* aux;                       // aux array 0 + tile + p*4 + (4 jg) 512        (floats)
+  uint8_t* sig;                     // sigma16 layer 0 + tile + p*16 + (2 jg) 2048
+  size_t dwl_stride, aux_stride, sig_stride;
+  int p, kcol;                      // kcol = 16 jg
+};
+struct EpiOps { uint4 s, b0, b1; };   // side-array operands of one sub-piece
+struct EpiStepPtrs {                  // per-step pointers (thread offsets included)
+  const uint8_t* sigp; uint8_t* sigw;
+  const uint8_t *dhi, *dlo;           // delta_l (dW layout) for S3
+  float* zb2;                         // zbar2_l
+  const float* part_in;               // partial sums consumed by this step
+  float* part_out;                    // RAW: partial sums produced
+  const float *bias, *wout;
+  float* hlast;
+  const float* e32;                   // aux e32 base WITHOUT the column-group offset (tile + p*4)
+};
+__device__ __forceinline__ uint32_t sub_a(int c, int h) { return (uint32_t)(8 * c + h) * A_LBO; }
+__device__ __forceinline__ uint32_t sub_d(int c, int h) { return (uint32_t)(8 * c + h) * 256u; }
+__device__ __forceinline__ uint32_t sub_x(int c, int h) { return (uint32_t)(16 * c + 2 * h) * 512u; }
+
+template <int kPasses>
+__device__ __forceinline__ void put8(const EpiT& T, const float* x, int c, int h, bool to_a, int dwl_arr) {
+  uint4 hi, lo;
+  if (kPasses == 3) split8(x, hi, lo); else hi = pack8_hi(x);
+  if (to_a) {
+    *reinterpret_cast<uint4*>(T.a_hi + sub_a(c, h)) = hi;
+    if (kPasses == 3) *reinterpret_cast<uint4*>(T.a_lo + sub_a(c, h)) = lo;
+  }
+  if (dwl_arr >= 0) {
+    const size_t off = (size_t)dwl_arr * T.dwl_stride + sub_d(c, h);
+    *reinterpret_cast<uint4*>(T.dwl_hi + off) = hi;
+    if (kPasses == 3) *reinterpret_cast<uint4*>(T.dwl_lo + off) = lo;
+  }
+}
+
+template <int EPI, int kPasses>
+__device__ __forceinline__ void epi_load(const EpiStepPtrs& P, bool l_is_cat, int c, int h, EpiOps& o) {
+  if (EPI == EPI_S2 || EPI == EPI_S3 || EPI == EPI_S3_LAST || EPI == EPI_S4)
+    o.s = *reinterpret_cast<const uint4*>(P.sigp + sub_a(c, h));
+  if (EPI == EPI_S3 || EPI == EPI_S3_LAST) {
+    o.b0 = *reinterpret_cast<const uint4*>(P.dhi + sub_d(c, h));
+    if (kPasses == 3) o.b1 = *reinterpret_cast<const uint4*>(P.dlo + sub_d(c, h));
+  } else if (EPI == EPI_S4) {
+    o.b0 = *reinterpret_cast<const uint4*>(P.zb2 + sub_x(c, h));
+    o.b1 = *reinterpret_cast<const uint4*>(P.zb2 + sub_x(c, h) + 512);
+  } else if (EPI == EPI_S2_END || ((EPI == EPI_S1 || EPI == EPI_S1_LAST) && l_is_cat)) {
+    o.b0 = *reinterpret_cast<const uint4*>(P.part_in + sub_x(c, h));
+    o.b1 = *reinterpret_cast<const uint4*>(P.part_in + sub_x(c, h) + 512);
+  }
+}
+
+struct EpiAcc { float raw_acc, gx, gy, gz; };
+
+template <int EPI, int kPasses>
+__device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, const EpiStepPtrs& P, const EpiOps& o,
+                                        uint32_t d_tmem, int c, int h, int l, bool l_is_cat, bool train, bool store_state,
+                                        bool last_step, float sbar, EpiAcc& acc) {
+  const int k0 = 64 * c + T.kcol + 8 * h;
+  float v[8];
+  tmem_ld8(d_tmem + k0, v);
+  if (EPI == EPI_RAW) {
+    st4(P.part_out + sub_x(c, h), v[0], v[1], v[2], v[3]);
+    st4(P.part_out + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
+  } else if (EPI == EPI_S1 || EPI == EPI_S1_LAST) {
+    const float4 ba = ld4(P.bias + k0), bb = ld4(P.bias + k0 + 4);
+    float z[8] = {v[0] + ba.x, v[1] + ba.y, v[2] + ba.z, v[3] + ba.w, v[4] + bb.x, v[5] + bb.y, v[6] + bb.z, v[7] + bb.w};
+    if (l_is_cat) {
+      z[0] += __uint_as_float(o.b0.x); z[1] += __uint_as_float(o.b0.y); z[2] += __uint_as_float(o.b0.z); z[3] += __uint_as_float(o.b0.w);
+      z[4] += __uint_as_float(o.b1.x); z[5] += __uint_as_float(o.b1.y); z[6] += __uint_as_float(o.b1.z); z[7] += __uint_as_float(o.b1.w);
+    }
+    float hh[8], sg[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) softplus100_fast(z[t], hh[t], sg[t]);
+    if (store_state) *reinterpret_cast<uint4*>(P.sigw + sub_a(c, h)) = pack_unorm16x8(sg);
+    if (EPI == EPI_S1) {
+      put8<kPasses>(T, hh, c, h, true, (train && l + 1 < args.L) ? args.arr_yh + l + 1 : -1);
+    } else {
+      const float4 wa = ld4(P.wout + k0), wb = ld4(P.wout + k0 + 4);
+      const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      if (train) {
+        st4(P.hlast + sub_x(c, h), hh[0], hh[1], hh[2], hh[3]);
+        st4(P.hlast + sub_x(c, h) + 512, hh[4], hh[5], hh[6], hh[7]);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        acc.raw_acc = fmaf(hh[t], ww[t], acc.raw_acc);
+        v[t] = args.scale_output * ww[t] * sg[t];          // delta_{L-1} = a_{L-1} * sigma
+      }
+      put8<kPasses>(T, v, c, h, args.mode != TC_MODE_FWD, train ? args.arr_xd + l : -1);
+    }
+  } else if (EPI == EPI_S2) {
+    float sg[8];
+    unpack_unorm16x8(o.s, sg);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] *= sg[t];
+    put8<kPasses>(T, v, c, h, true, train ? args.arr_xd + l : -1);
+  } else if (EPI == EPI_S2_END) {
+    const int half = ISDFB_NDIRS * args.pe.n_freqs;
+    const float a[8] = {v[0] + __uint_as_float(o.b0.x), v[1] + __uint_as_float(o.b0.y), v[2] + __uint_as_float(o.b0.z), v[3] + __uint_as_float(o.b0.w),
+                        v[4] + __uint_as_float(o.b1.x), v[5] + __uint_as_float(o.b1.y), v[6] + __uint_as_float(o.b1.z), v[7] + __uint_as_float(o.b1.w)};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int k = k0 + t;
+      if (k < 3) {
+        if (k == 0) acc.gx += a[t]; else if (k == 1) acc.gy += a[t]; else acc.gz += a[t];
+      } else if (k < args.E) {
+        const bool first = (k - 3) < half;
+        const int km = first ? k + half : k - half;
+        const float mate = P.e32[(km >> 2) * 512 + (km & 3)];
+        // d sin(xb)/d xb = "cos" = e[mate];  d sin(xb+pi/2)/d xb = -sin(xb) = -e[mate]
+        const float w = (first ? mate : -mate) * (float)(1 << args.feat_f[k]) * a[t];
+        const int d = args.feat_d[k];
+        acc.gx = fmaf(w, c_ico[d][0], acc.gx);
+        acc.gy = fmaf(w, c_ico[d][1], acc.gy);
+        acc.gz = fmaf(w, c_ico[d][2], acc.gz);
+      }
+    }
+  } else if (EPI == EPI_S3 || EPI == EPI_S3_LAST) {
+    float sg[8], dl[8], zb[8];
+    unpack_unorm16x8(o.s, sg);
+    unpack8(o.b0, dl);
+    if (kPasses == 3) {
+      float t8[8];
+      unpack8(o.b1, t8);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) dl[t] += t8[t];
+    }
+    if (l_is_cat) {
+      const float4 pa = ld4(P.part_in + sub_x(c, h)), pb = ld4(P.part_in + sub_x(c, h) + 512);
+      v[0] += pa.x; v[1] += pa.y; v[2] += pa.z; v[3] += pa.w; v[4] += pb.x; v[5] += pb.y; v[6] += pb.z; v[7] += pb.w;
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float om = 100.f * (1.f - sg[t]);   // sigma' / sigma; 0 in the saturated (linear) regime
+      zb[t] = v[t] * dl[t] * om;           // zbar2 = dbar * delta * beta (1 - sigma)
+      v[t] = v[t] * sg[t];                 // abar = dbar * sigma
+    }
+    if (EPI == EPI_S3) {
+      st4(P.zb2 + sub_x(c, h), zb[0], zb[1], zb[2], zb[3]);
+      st4(P.zb2 + sub_x(c, h) + 512, zb[4], zb[5], zb[6], zb[7]);
+      put8<kPasses>(T, v, c, h, true, (l + 1 < args.L) ? args.arr_ya + l + 1 : -1);
+    } else {
+      // v_blob = sbar * h_last + abar_last  (for d w_out);  A <- zbar_last = sbar c w_out sigma + zbar2
+      const float4 ha = ld4(P.hlast + sub_x(c, h)), hb = ld4(P.hlast + sub_x(c, h) + 512);
+      const float4 wa = ld4(P.wout + k0), wb = ld4(P.wout + k0 + 4);
+      const float hh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+      const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      float vb[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        vb[t] = fmaf(sbar, hh[t], v[t]);
+        zb[t] = fmaf(sbar * args.scale_output * ww[t], sg[t], zb[t]);
+      }
+      put8<kPasses>(T, vb, c, h, false, args.arr_v);
+      put8<kPasses>(T, zb, c, h, true, args.arr_xz + l);
+    }
+  } else {   // EPI_S4
+    float sg[8];
+    unpack_unorm16x8(o.s, sg);
+    const float z2[8] = {__uint_as_float(o.b0.x), __uint_as_float(o.b0.y), __uint_as_float(o.b0.z), __uint_as_float(o.b0.w),
+                         __uint_as_float(o.b1.x), __uint_as_float(o.b1.y), __uint_as_float(o.b1.z), __uint_as_float(o.b1.w)};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = fmaf(v[t], sg[t], z2[t]);
+    put8<kPasses>(T, v, c, h, !last_step, args.arr_xz + l);
+  }
+}
+
+// one whole step of the epilogue for this thread (8 sub-pieces), operands fetched one sub-piece ahead
+template <int EPI, int kPasses>
+__device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T, const EpiStepPtrs& P, ChainSmemTail* tail,
+                                         uint32_t d_tmem, uint32_t n, int l, bool train, bool store_state, bool last_step,
+                                         float sbar, EpiAcc& acc, int lane) {
+  const bool l_is_cat = (l == args.ic);
+  EpiOps oa, ob;
+  oa.s = oa.b0 = oa.b1 = ob.s = ob.b0 = ob.b1 = make_uint4(0, 0, 0, 0);
+  epi_load<EPI, kPasses>(P, l_is_cat, 0, 0, oa);            // overlaps the tail of this step's MMA
+  mbar_wait(smem_u32(&tail->d_full[n & 1]), (n >> 1) & 1);
+  tc_fence_after();
+  if (EPI == EPI_RAW) {
+    // A is left untouched: release the next step now (its MMA overlaps this drain of D into a side
+    // array).  Arriving only after d_full guarantees every warp finished the previous phase.
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mbar_arrive(smem_u32(&tail->a_ready[c]));
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    epi_load<EPI, kPasses>(P, l_is_cat, c, 1, ob);
+    epi_sub<EPI, kPasses>(args, T, P, oa, d_tmem, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
+    if (c < 3) epi_load<EPI, kPasses>(P, l_is_cat, c + 1, 0, oa);
+    epi_sub<EPI, kPasses>(args, T, P, ob, d_tmem, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
+    if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
+    }
+  }
+  tc_fence_before();
+}
+
 template <int kPasses>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_constant__ TcChainArgs args) {
   using Cfg = ChainCfg<kPasses>;
@@ -152,46 +361,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
     }
   } else {
     // ===================== epilogue: thread = (point, 4 x 16 columns) =====================
-    // Warp (q, j) owns points 32q..32q+31 and, inside every 64-column K chunk c of the next A operand,
-    // columns [64c+16j, 64c+16j+16): chunk 0 is complete after a quarter of the epilogue, so the MMA of
-    // the next step runs under the rest of it.  Work unit = 8 columns ("sub-piece"); the side-array
-    // loads of sub-piece i+1 are issued before the stores of sub-piece i (software prefetch).
+    // Warp (q, jg) owns points 32q..32q+31 and, inside every 64-column K chunk c of the next A operand,
+    // columns [64c+16jg, 64c+16jg+16): chunk 0 is complete after a quarter of the epilogue, so the MMA
+    // of the next step runs under the rest of it.
     const int q = warp & 3, jg = warp >> 2;
     const int p = q * 32 + lane;                                  // row / TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float c_out = args.scale_output;
     const float* Wp = args.w_packed;
-    const int L = args.L, ic = args.ic, E = args.E;
+    const int E = args.E;
     const int half = ISDFB_NDIRS * args.pe.n_freqs;
     const bool train = args.mode == TC_MODE_TRAIN;
     const bool store_state = args.mode != TC_MODE_FWD;
     uint32_t n = 0;
     float lsum0 = 0.f, lsum1 = 0.f, lsum2 = 0.f, lsum3 = 0.f, sbsum = 0.f;
-    auto col_of = [&](int i) { return (i >> 1) * 64 + jg * 16 + (i & 1) * 8; };
 
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int64_t pl = (int64_t)tile * TC_TILE + p;             // point index inside the chunk
       const bool real = pl < args.n_points;
-      const size_t tile_aux = (size_t)tile * TC_TILE_FLOATS;
-      const size_t tile_dwl = (size_t)tile * TC_DWL_TILE_BYTES;
-      auto aux_ptr = [&](int arr) { return args.aux + (size_t)arr * args.aux_stride + tile_aux; };
-      auto sig_ptr = [&](int l_) { return args.sig16 + (size_t)l_ * args.sig16_stride + tile_dwl; };
-      // write 8 consecutive features [k0, k0+8) of this point: A operand image and/or a dW-layout copy
-      auto put8 = [&](const float* x, int k0, bool to_a, int dwl_arr) {
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        if (to_a) {
-          const uint32_t off = (uint32_t)(k0 >> 3) * A_LBO + (uint32_t)p * 16u;
-          *reinterpret_cast<uint4*>(a_hi + off) = hi;
-          if (kPasses == 3) *reinterpret_cast<uint4*>(a_lo + off) = lo;
-        }
-        if (dwl_arr >= 0) {
-          const size_t off = (size_t)dwl_arr * args.dwl_stride + tile_dwl + dwl_off_bytes(k0, p);
-          *reinterpret_cast<uint4*>(args.dwl_hi + off) = hi;
-          if (kPasses == 3) *reinterpret_cast<uint4*>(args.dwl_lo + off) = lo;
-        }
-      };
+      EpiT T;
+      T.p = p; T.kcol = 16 * jg;
+      T.a_hi = a_hi + p * 16 + (2 * jg) * A_LBO;
+      T.a_lo = a_lo + p * 16 + (2 * jg) * A_LBO;
+      const size_t dthr = (size_t)tile * TC_DWL_TILE_BYTES + (size_t)(p >> 4) * 8192u + (size_t)(p & 15) * 16u + (size_t)(2 * jg) * 256u;
+      T.dwl_hi = args.dwl_hi + dthr;
+      T.dwl_lo = args.dwl_lo + dthr;
+      T.aux = args.aux + (size_t)tile * TC_TILE_FLOATS + p * 4 + (4 * jg) * 512;
+      T.sig = args.sig16 + (size_t)tile * TC_DWL_TILE_BYTES + p * 16 + (2 * jg) * 2048;
+      T.dwl_stride = args.dwl_stride; T.aux_stride = args.aux_stride; T.sig_stride = args.sig16_stride;
+      const float* e32_thr = args.aux + (size_t)args.arr_e32 * args.aux_stride + (size_t)tile * TC_TILE_FLOATS + p * 4;
+      float* e32_w = T.aux + (size_t)args.arr_e32 * args.aux_stride;
       auto chunk_ready = [&](int c) {
         fence_proxy_async_smem();
         __syncwarp();
@@ -204,10 +404,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         const float* xp = args.x + pl * 3;
         pe_scale_input(args.pe, xp[0], xp[1], xp[2], xs);
       }
-      float* e32 = aux_ptr(args.arr_e32);
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {
-        const int k0 = col_of(i);
+        const int c = i >> 1, h = i & 1;
+        const int k0 = 64 * c + T.kcol + 8 * h;
         float v[8];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
@@ -223,16 +423,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
           }
           v[jj] = val;
         }
-        put8(v, k0, true, train ? args.arr_yh : -1);
+        put8<kPasses>(T, v, c, h, true, train ? args.arr_yh : -1);
         if (store_state) {
-          st4(e32 + aux_off_floats(k0, p), v[0], v[1], v[2], v[3]);
-          st4(e32 + aux_off_floats(k0 + 4, p), v[4], v[5], v[6], v[7]);
+          st4(e32_w + sub_x(c, h), v[0], v[1], v[2], v[3]);
+          st4(e32_w + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
         }
-        if (i & 1) chunk_ready(i >> 1);
+        if (h) chunk_ready(c);
       }
 
       // per-point state carried across steps
       float sdf_reg = 0.f, sbar = 0.f, u3[3] = {0.f, 0.f, 0.f};
+      const bool dbg = args.dbg_clock && blockIdx.x == 0 && threadIdx.x == 0 && it == 0;
+      if (dbg) args.dbg_clock[0] = clock64();
 
       for (int s = 0; s < n_steps; ++s, ++n) {
         const TcStep st = args.steps[s];
@@ -240,171 +442,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         const int epi = st.epi;
         const bool last_step = (s == n_steps - 1);
         const uint32_t d_tmem = tmem + (n & 1) * 256 + lane_addr;
-        const bool use_sig = (epi == EPI_S2 || epi == EPI_S3 || epi == EPI_S3_LAST || epi == EPI_S4);
-        const bool use_delta = (epi == EPI_S3 || epi == EPI_S3_LAST);
-        const uint8_t* sigp = sig_ptr(l);
-        float* zb2 = aux_ptr(args.arr_zb2 + l);
-        const float* part_in = aux_ptr(args.arr_part + (epi == EPI_S2_END ? 1 : 0));
-        const size_t doff = (size_t)(args.arr_xd + l) * args.dwl_stride + tile_dwl;
-        const bool use_part01 = (epi == EPI_S2_END) || ((epi == EPI_S1 || epi == EPI_S1_LAST) && l == ic);
-        // side-array operands of one sub-piece (12 registers), fetched one sub-piece ahead
-        uint4 nx_s = make_uint4(0, 0, 0, 0), nx_b0 = nx_s, nx_b1 = nx_s;
-        auto prefetch = [&](int k0) {
-          if (use_sig) nx_s = *reinterpret_cast<const uint4*>(sigp + (uint32_t)(k0 >> 3) * 2048u + (uint32_t)p * 16u);
-          if (use_delta) {
-            const uint32_t o = dwl_off_bytes(k0, p);
-            nx_b0 = *reinterpret_cast<const uint4*>(args.dwl_hi + doff + o);
-            if (kPasses == 3) nx_b1 = *reinterpret_cast<const uint4*>(args.dwl_lo + doff + o);
-          } else if (epi == EPI_S4) {
-            nx_b0 = *reinterpret_cast<const uint4*>(zb2 + aux_off_floats(k0, p));
-            nx_b1 = *reinterpret_cast<const uint4*>(zb2 + aux_off_floats(k0 + 4, p));
-          } else if (use_part01) {
-            nx_b0 = *reinterpret_cast<const uint4*>(part_in + aux_off_floats(k0, p));
-            nx_b1 = *reinterpret_cast<const uint4*>(part_in + aux_off_floats(k0 + 4, p));
-          }
-        };
-        prefetch(col_of(0));                      // overlaps the tail of this step's MMA
-        mbar_wait(smem_u32(&tail->d_full[n & 1]), (n >> 1) & 1);
-        tc_fence_after();
-        if (epi == EPI_RAW) {
-          // A is left untouched: release the next step now (its MMA overlaps this drain of D into a
-          // side array).  Arriving only after d_full guarantees every warp finished the previous phase.
-          __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) mbar_arrive(smem_u32(&tail->a_ready[c]));
-          }
+        EpiStepPtrs P;
+        P.sigp = T.sig + (size_t)l * T.sig_stride;
+        P.sigw = T.sig + (size_t)l * T.sig_stride;
+        P.dhi = T.dwl_hi + (size_t)(args.arr_xd + l) * T.dwl_stride;
+        P.dlo = T.dwl_lo + (size_t)(args.arr_xd + l) * T.dwl_stride;
+        P.zb2 = T.aux + (size_t)(args.arr_zb2 + l) * T.aux_stride;
+        P.part_in = T.aux + (size_t)(args.arr_part + (epi == EPI_S2_END ? 1 : ((epi == EPI_S3 || epi == EPI_S3_LAST) ? 2 : 0))) * T.aux_stride;
+        P.part_out = T.aux + (size_t)(args.arr_part + st.aux) * T.aux_stride;
+        P.bias = Wp + args.lay_b_off[l];
+        P.wout = Wp + args.wout_off;
+        P.hlast = T.aux + (size_t)args.arr_hlast * T.aux_stride;
+        P.e32 = e32_thr;
+        EpiAcc acc = {0.f, 0.f, 0.f, 0.f};
+        if (dbg) args.dbg_clock[1 + 2 * s] = clock64();
+        switch (epi) {
+          case EPI_RAW:     epi_step<EPI_RAW, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S1:      epi_step<EPI_S1, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S1_LAST: epi_step<EPI_S1_LAST, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S2:      epi_step<EPI_S2, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S2_END:  epi_step<EPI_S2_END, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S3:      epi_step<EPI_S3, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S3_LAST: epi_step<EPI_S3_LAST, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          default:          epi_step<EPI_S4, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
         }
 
-        const float* bias = Wp + args.lay_b_off[l];
-        float raw_acc = 0.f;                      // S1_LAST: h . w_out (this thread's 64 columns)
-        float gx = 0.f, gy = 0.f, gz = 0.f;       // S2_END: PE back-projection accumulators
-
-#pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
-          const int k0 = col_of(i);
-          const uint4 cs = nx_s, cb0 = nx_b0, cb1 = nx_b1;
-          if (i + 1 < 8) prefetch(col_of(i + 1));
-          float v[8];
-          tmem_ld8(d_tmem + k0, v);
-          if (epi == EPI_RAW) {
-            float* dst = aux_ptr(args.arr_part + st.aux);
-            st4(dst + aux_off_floats(k0, p), v[0], v[1], v[2], v[3]);
-            st4(dst + aux_off_floats(k0 + 4, p), v[4], v[5], v[6], v[7]);
-          } else if (epi == EPI_S1 || epi == EPI_S1_LAST) {
-            const float4 ba = ld4(bias + k0), bb = ld4(bias + k0 + 4);
-            float z[8] = {v[0] + ba.x, v[1] + ba.y, v[2] + ba.z, v[3] + ba.w, v[4] + bb.x, v[5] + bb.y, v[6] + bb.z, v[7] + bb.w};
-            if (l == ic) {
-              z[0] += __uint_as_float(cb0.x); z[1] += __uint_as_float(cb0.y); z[2] += __uint_as_float(cb0.z); z[3] += __uint_as_float(cb0.w);
-              z[4] += __uint_as_float(cb1.x); z[5] += __uint_as_float(cb1.y); z[6] += __uint_as_float(cb1.z); z[7] += __uint_as_float(cb1.w);
-            }
-            float h[8], sg[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) softplus100_fast(z[t], h[t], sg[t]);
-            if (store_state)
-              *reinterpret_cast<uint4*>(args.sig16 + (size_t)l * args.sig16_stride + tile_dwl + (uint32_t)(k0 >> 3) * 2048u + (uint32_t)p * 16u) = pack_unorm16x8(sg);
-            if (epi == EPI_S1) {
-              put8(h, k0, true, (train && l + 1 < L) ? args.arr_yh + l + 1 : -1);
-            } else {
-              const float* wout = Wp + args.wout_off;
-              const float4 wa = ld4(wout + k0), wb = ld4(wout + k0 + 4);
-              const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-              if (train) {
-                float* hl = aux_ptr(args.arr_hlast);
-                st4(hl + aux_off_floats(k0, p), h[0], h[1], h[2], h[3]);
-                st4(hl + aux_off_floats(k0 + 4, p), h[4], h[5], h[6], h[7]);
-              }
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                raw_acc = fmaf(h[t], ww[t], raw_acc);
-                // delta_{L-1} = a_{L-1} * sigma, with sigma as the later sweeps will read it back
-                v[t] = c_out * ww[t] * sg[t];
-              }
-              put8(v, k0, args.mode != TC_MODE_FWD, train ? args.arr_xd + l : -1);
-            }
-          } else if (epi == EPI_S2) {
-            float sg[8];
-            unpack_unorm16x8(cs, sg);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] *= sg[t];
-            put8(v, k0, true, train ? args.arr_xd + l : -1);
-          } else if (epi == EPI_S2_END) {
-            const float a[8] = {v[0] + __uint_as_float(cb0.x), v[1] + __uint_as_float(cb0.y), v[2] + __uint_as_float(cb0.z), v[3] + __uint_as_float(cb0.w),
-                                v[4] + __uint_as_float(cb1.x), v[5] + __uint_as_float(cb1.y), v[6] + __uint_as_float(cb1.z), v[7] + __uint_as_float(cb1.w)};
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const int k = k0 + t;
-              if (k < 3) {
-                if (k == 0) gx += a[t]; else if (k == 1) gy += a[t]; else gz += a[t];
-              } else if (k < E) {
-                const bool first = (k - 3) < half;
-                const float mate = e32[aux_off_floats(first ? k + half : k - half, p)];
-                // d sin(xb)/d xb = "cos" = e[mate];  d sin(xb+pi/2)/d xb = -sin(xb) = -e[mate]
-                const float w = (first ? mate : -mate) * (float)(1 << args.feat_f[k]) * a[t];
-                const int d = args.feat_d[k];
-                gx = fmaf(w, c_ico[d][0], gx);
-                gy = fmaf(w, c_ico[d][1], gy);
-                gz = fmaf(w, c_ico[d][2], gz);
-              }
-            }
-          } else if (epi == EPI_S3 || epi == EPI_S3_LAST) {
-            float sg[8], dl[8], zb[8];
-            unpack_unorm16x8(cs, sg);
-            unpack8(cb0, dl);
-            if (kPasses == 3) {
-              float t8[8];
-              unpack8(cb1, t8);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) dl[t] += t8[t];
-            }
-            if (l == ic) {
-              const float* part = aux_ptr(args.arr_part + 2);
-              const float4 pa = ld4(part + aux_off_floats(k0, p)), pb = ld4(part + aux_off_floats(k0 + 4, p));
-              v[0] += pa.x; v[1] += pa.y; v[2] += pa.z; v[3] += pa.w; v[4] += pb.x; v[5] += pb.y; v[6] += pb.z; v[7] += pb.w;
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const float om = (sg[t] >= 1.f) ? 0.f : 100.f * (1.f - sg[t]);
-              zb[t] = v[t] * dl[t] * om;           // zbar2 = dbar * delta * beta (1 - sigma)
-              v[t] = v[t] * sg[t];                 // abar = dbar * sigma
-            }
-            if (epi == EPI_S3) {
-              st4(zb2 + aux_off_floats(k0, p), zb[0], zb[1], zb[2], zb[3]);
-              st4(zb2 + aux_off_floats(k0 + 4, p), zb[4], zb[5], zb[6], zb[7]);
-              put8(v, k0, true, (l + 1 < L) ? args.arr_ya + l + 1 : -1);
-            } else {
-              // v_blob = sbar * h_last + abar_last  (for d w_out);  A <- zbar_last = sbar c w_out sigma + zbar2
-              const float* wout = Wp + args.wout_off;
-              const float* hl = aux_ptr(args.arr_hlast);
-              const float4 ha = ld4(hl + aux_off_floats(k0, p)), hb = ld4(hl + aux_off_floats(k0 + 4, p));
-              const float4 wa = ld4(wout + k0), wb = ld4(wout + k0 + 4);
-              const float hh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-              const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-              float vb[8];
-#pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                vb[t] = fmaf(sbar, hh[t], v[t]);
-                zb[t] = fmaf(sbar * c_out * ww[t], sg[t], zb[t]);
-              }
-              put8(vb, k0, false, args.arr_v);
-              put8(zb, k0, true, args.arr_xz + l);
-            }
-          } else {   // EPI_S4
-            float sg[8];
-            unpack_unorm16x8(cs, sg);
-            const float z2[8] = {__uint_as_float(cb0.x), __uint_as_float(cb0.y), __uint_as_float(cb0.z), __uint_as_float(cb0.w),
-                                 __uint_as_float(cb1.x), __uint_as_float(cb1.y), __uint_as_float(cb1.z), __uint_as_float(cb1.w)};
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = fmaf(v[t], sg[t], z2[t]);
-            put8(v, k0, !last_step, args.arr_xz + l);
-          }
-          if ((i & 1) && epi != EPI_RAW && epi != EPI_S2_END && !last_step) chunk_ready(i >> 1);
-        }
-        tc_fence_before();
-
+        if (dbg) args.dbg_clock[2 + 2 * s] = clock64();
         if (epi == EPI_S1_LAST) {
           // out layer: combine the four column groups of every point
-          red[jg * 128 + p] = raw_acc;
+          red[jg * 128 + p] = acc.raw_acc;
           named_bar_sync(1, EPI_THREADS);
           if (jg == 0) {
             float raw = red[p] + red[128 + p] + red[256 + p] + red[384 + p] + Wp[args.bout_off];
@@ -413,14 +479,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             if (real) args.sdf_out[pl] = sdf_reg;
           }
         } else if (epi == EPI_S2_END) {
-          red[(0 * 4 + jg) * 128 + p] = gx;
-          red[(1 * 4 + jg) * 128 + p] = gy;
-          red[(2 * 4 + jg) * 128 + p] = gz;
+          red[(0 * 4 + jg) * 128 + p] = acc.gx;
+          red[(1 * 4 + jg) * 128 + p] = acc.gy;
+          red[(2 * 4 + jg) * 128 + p] = acc.gz;
           named_bar_sync(1, EPI_THREADS);
           if (jg == 0) {
-            gx = red[p] + red[128 + p] + red[256 + p] + red[384 + p];
-            gy = red[512 + p] + red[640 + p] + red[768 + p] + red[896 + p];
-            gz = red[1024 + p] + red[1152 + p] + red[1280 + p] + red[1408 + p];
+            const float gx = red[p] + red[128 + p] + red[256 + p] + red[384 + p];
+            const float gy = red[512 + p] + red[640 + p] + red[768 + p] + red[896 + p];
+            const float gz = red[1024 + p] + red[1152 + p] + red[1280 + p] + red[1408 + p];
             float ox = gx, oy = gy, oz = gz;     // g = s R^T g_xs
             if (args.pe.has_transform) {
               ox = args.pe.R[0] * gx + args.pe.R[3] * gy + args.pe.R[6] * gz;
@@ -445,10 +511,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
                   if (jx == 0 && args.normals) {
                     uu[0] = args.normals[r * 3]; uu[1] = args.normals[r * 3 + 1]; uu[2] = args.normals[r * 3 + 2];
                   } else {
-                    const float* T = args.T_WC + r * 16;
-                    uu[0] = -(T[0] * dc[0] + T[1] * dc[1] + T[2] * dc[2]);
-                    uu[1] = -(T[4] * dc[0] + T[5] * dc[1] + T[6] * dc[2]);
-                    uu[2] = -(T[8] * dc[0] + T[9] * dc[1] + T[10] * dc[2]);
+                    const float* Tm = args.T_WC + r * 16;
+                    uu[0] = -(Tm[0] * dc[0] + Tm[1] * dc[1] + Tm[2] * dc[2]);
+                    uu[1] = -(Tm[4] * dc[0] + Tm[5] * dc[1] + Tm[6] * dc[2]);
+                    uu[2] = -(Tm[8] * dc[0] + Tm[9] * dc[1] + Tm[10] * dc[2]);
                   }
                   const LossPoint o = loss_point(args.loss, sdf_reg, g, bnd, uu);
                   sb = o.sbar; gb[0] = o.gbar[0]; gb[1] = o.gbar[1]; gb[2] = o.gbar[2];
@@ -475,7 +541,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             // abar_e -> A operand of S3 (second pass over this thread's columns)
 #pragma unroll 1
             for (int i = 0; i < 8; ++i) {
-              const int k0 = col_of(i);
+              const int c = i >> 1, h = i & 1;
+              const int k0 = 64 * c + T.kcol + 8 * h;
               float v[8];
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
@@ -487,13 +554,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
                   const int d = args.feat_d[k];
                   const float ud = (u3[0] * c_ico[d][0] + u3[1] * c_ico[d][1] + u3[2] * c_ico[d][2]) * (float)(1 << args.feat_f[k]);
                   const bool first = (k - 3) < half;
-                  const float mate = e32[aux_off_floats(first ? k + half : k - half, p)];
+                  const int km = first ? k + half : k - half;
+                  const float mate = e32_thr[(km >> 2) * 512 + (km & 3)];
                   val = first ? ud * mate : -ud * mate;
                 }
                 v[jj] = val;
               }
-              put8(v, k0, true, args.arr_ya);
-              if (i & 1) chunk_ready(i >> 1);
+              put8<kPasses>(T, v, c, h, true, args.arr_ya);
+              if (h) chunk_ready(c);
             }
           }
         }

@@ -48,6 +48,7 @@ struct TcChainArgs {
   size_t dwl_stride;         // bytes between arrays
   int32_t arr_zb2, arr_part, arr_e32, arr_hlast;            // aux array indices
   int32_t arr_yh, arr_ya, arr_xd, arr_xz, arr_v;            // dW-layout array indices
+  long long* dbg_clock;                                     // optional: per-step timeline of CTA 0 (tests)
   uint8_t feat_d[TC_H], feat_f[TC_H];                       // PE column -> (direction, octave)
 };
 

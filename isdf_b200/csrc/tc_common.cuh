@@ -141,36 +141,45 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// sigma in [0,1] as unorm16 (abs error 7.6e-6; 0 and 1 exact): 8 values <-> 16 B
+// sigma in [0,1] as unorm16 (abs error 7.6e-6; 0 and 1 exact): 8 values <-> 16 B.
+// Conversions stay on the FMA/ALU pipes (magic-number rounding), not on the quarter-rate XU pipe.
 __device__ __forceinline__ uint4 pack_unorm16x8(const float* s) {
   uint32_t w[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const uint32_t a = __float2uint_rn(s[2 * i] * 65535.f), b = __float2uint_rn(s[2 * i + 1] * 65535.f);
-    w[i] = a | (b << 16);
+    const uint32_t a = __float_as_uint(fmaf(s[2 * i], 65535.f, 8388608.f));       // 2^23 + rint(65535 s)
+    const uint32_t b = __float_as_uint(fmaf(s[2 * i + 1], 65535.f, 8388608.f));
+    w[i] = __byte_perm(a, b, 0x5410);                                              // low halves of a, b
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 __device__ __forceinline__ void unpack_unorm16x8(const uint4& v, float* s) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const float c = 1.52590236e-05f;            // nextafter(1/65535): 65535 c >= 1, clamped below
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    s[2 * i] = (float)(w[i] & 0xFFFFu) * (1.f / 65535.f);
-    s[2 * i + 1] = (float)(w[i] >> 16) * (1.f / 65535.f);
+    const float a = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7610)) - 8388608.f;
+    const float b = __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7632)) - 8388608.f;
+    s[2 * i] = fminf(a * c, 1.f);
+    s[2 * i + 1] = fminf(b * c, 1.f);
   }
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// softplus(beta=100, threshold=20) and sigmoid(100 z) on the SFU (ex2 / lg2 / rcp approximations:
-// relative error ~2^-22, far below the bf16x3 product error)
+// softplus(beta=100) and sigmoid(100 z), branch-free, three SFU ops (ex2 / lg2 / rcp approximations,
+// relative error ~2^-22, far below the bf16x3 product error).  Stable form: t = exp(-|bz|) in (0,1],
+// softplus = max(z,0) + log(1+t)/beta, sigmoid = (bz >= 0 ? 1 : t) / (1+t).  For bz > 20 this gives
+// z + O(1e-11) and sigma == 1.0f, i.e. torch's threshold branch (fc_map.py:54) to fp32 rounding.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void softplus100_fast(float z, float& h, float& sig) {
-  const float bz = 100.f * z;
-  const float t = __expf(fminf(bz, 30.f));
+  const float t = ex2_approx(fabsf(z) * -144.26950408889634f);      // exp(-|100 z|)
   const float u = 1.f + t;
-  const bool lin = bz > 20.f;
-  sig = lin ? 1.f : __fdividef(t, u);
-  h = lin ? z : __logf(u) * 0.01f;
+  const float r = rcp_approx(u);
+  sig = (z >= 0.f) ? r : t * r;
+  h = fmaf(lg2_approx(u), 0.0069314718055994531f, fmaxf(z, 0.f));   // + ln(2)/100 * log2(1+t)
 }
 
 // ---- descriptors --------------------------------------------------------------------------------
@@ -197,13 +206,27 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
-// eight fp32 -> 16 B of bf16 hi and 16 B of bf16 lo
+// two fp32 -> packed bf16x2 (x0 in the low half), round-to-nearest-even, one instruction
+__device__ __forceinline__ uint32_t cvt_bf16x2(float x0, float x1) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x1), "f"(x0));
+  return d;
+}
+// eight fp32 -> 16 B of bf16 hi and 16 B of bf16 lo  (lo = bf16(x - float(hi)))
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-  __nv_bfloat16 h[8], l[8];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) split_bf16(x[i], h[i], l[i]);
-  hi = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-  lo = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+  for (int i = 0; i < 4; ++i) {
+    h[i] = cvt_bf16x2(x[2 * i], x[2 * i + 1]);
+    const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);
+    const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
+    l[i] = cvt_bf16x2(r0, r1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ uint4 pack8_hi(const float* x) {
+  return make_uint4(cvt_bf16x2(x[0], x[1]), cvt_bf16x2(x[2], x[3]), cvt_bf16x2(x[4], x[5]), cvt_bf16x2(x[6], x[7]));
 }
 __device__ __forceinline__ void unpack8(const uint4& v, float* x) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};

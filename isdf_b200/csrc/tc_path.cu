@@ -67,12 +67,17 @@ int tc_create(isdfb_ctx* ctx) {
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->sig16, tc->dwl_stride * L));
   if (ctx->cfg.precision == ISDFB_PREC_BF16X3) ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dwl_lo, tc->dwl_stride * tc->n_dwl));
 
+  if (getenv("ISDFB_DEBUG_CLOCK")) {
+    ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dbg_clock, 128 * sizeof(long long)));
+    ISDFB_CUDA_OK(ctx, cudaMemset(tc->dbg_clock, 0, 128 * sizeof(long long)));
+  }
   for (int mode = 0; mode < 3; ++mode) {
     TcChainArgs& a = tc->proto[mode];
     memset(&a, 0, sizeof(a));
     build_program(lay, mode, a);
     a.mode = mode; a.L = L; a.ic = ic; a.E = lay.E;
     a.prefetch = getenv("ISDFB_NO_PREFETCH") ? 0 : 1;
+    a.dbg_clock = tc->dbg_clock;
     a.pe = ctx->pe;
     a.scale_output = ctx->cfg.scale_output;
     a.w_img = tc->w_img;
@@ -212,6 +217,14 @@ extern "C" int isdfb_debug_buffers(isdfb_ctx* ctx, float** aux, int64_t* aux_str
   *aux = tc->aux; *aux_stride_floats = (int64_t)tc->aux_stride;
   *dwl_hi = tc->dwl_hi; *dwl_lo = tc->dwl_lo; *dwl_stride_bytes = (int64_t)tc->dwl_stride;
   *n_aux = tc->n_aux; *n_dwl = tc->n_dwl; *tiles_cap = tc->tiles_cap; *sig16 = tc->sig16;
+  if (tc->dbg_clock) {   // debug timeline: printed by the host on request
+    long long h[128];
+    cudaMemcpy(h, tc->dbg_clock, sizeof(h), cudaMemcpyDeviceToHost);
+    const int ns = tc->proto[TC_MODE_TRAIN].n_steps;
+    printf("[isdfb] CTA0 tile0 timeline (cycles): PE_end=0");
+    for (int s = 0; s < ns; ++s) printf(" | s%d epi%d wait_end=%lld epi_end=%lld", s, tc->proto[TC_MODE_TRAIN].steps[s].epi, h[1 + 2 * s] - h[0], h[2 + 2 * s] - h[0]);
+    printf("\n");
+  }
   return ISDFB_OK;
 }
 

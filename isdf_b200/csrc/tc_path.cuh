@@ -43,6 +43,7 @@ struct TcState {
   cudaEvent_t ev[TC_PROF_MAX][3];   // before chain, after chain, after dW
   int ev_kind[TC_PROF_MAX];         // 1: chain only, 2: chain + dW
   int n_ev;
+  long long* dbg_clock;    // device buffer [128] when ISDFB_DEBUG_CLOCK is set
 };
 
 int tc_dw_launch(isdfb_ctx* ctx, const TcDwArgs& args, int passes, int grid, cudaStream_t st);

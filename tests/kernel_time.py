@@ -20,3 +20,10 @@ for i in range(10):
     eng.zero_grad(); eng.train_fwd_bwd(b['pc'],b['z_vals'],b['depth_sample'],b['dirs_C_sample'],b['T_WC_sample'],b['norm_sample'],nz,lc)
 pr=eng.profile_read()
 print(mode,R,'chain ms %.3f dw ms %.3f'%(pr['chain_ms']/pr['n_chain'],pr['dw_ms']/pr['n_dw']))
+x=b['pc'].reshape(-1,3).contiguous()
+for want in (False, True):
+    for i in range(3): eng.forward(x, want_grad=want)
+    eng.profile(True)
+    for i in range(10): eng.forward(x, want_grad=want)
+    pr=eng.profile_read()
+    print(mode,R,'forward%s chain ms %.3f (%d steps)'%('+grad' if want else '', pr['chain_ms']/pr['n_chain'], 14 if want else 7))
