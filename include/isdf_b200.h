@@ -161,6 +161,12 @@ int isdfb_frame_bins(isdfb_ctx* ctx, const float* loss_mat, const uint8_t* ray_v
 int isdfb_adamw(isdfb_ctx* ctx, float* params_flat, float* m, float* v, int64_t step, float lr,
                 float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                 void* stream);
+/* CUDA-graph-safe K6: the 1-based step counter lives on the device (advanced by the call itself), so a
+ * captured Trainer.step() replays with the right bias correction.  isdfb_adamw_set_step (synchronous)
+ * aligns it with a host-side count (state_dict load, switching from isdfb_adamw).                  */
+int isdfb_adamw_graph(isdfb_ctx* ctx, float* params_flat, float* m, float* v, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+int isdfb_adamw_set_step(isdfb_ctx* ctx, int64_t step, void* stream);
 /* ctx-internal gradient buffer (fp32, padded internal layout) for the NCCL all-reduce.     */
 int isdfb_grad_buffer(isdfb_ctx* ctx, float** ptr, int64_t* n_floats);
 

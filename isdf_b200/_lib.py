@@ -57,6 +57,8 @@ SIGNATURES = {
     "isdfb_export_grads": (C.c_int, [P, P, P]),
     "isdfb_frame_bins": (C.c_int, [P, P, P, P, P, P, I64, I32, I32, I32, I32, I32, P, P, P]),
     "isdfb_adamw": (C.c_int, [P, P, P, P, I64, F, F, F, F, F, F, P]),
+    "isdfb_adamw_graph": (C.c_int, [P, P, P, P, F, F, F, F, F, F, P]),
+    "isdfb_adamw_set_step": (C.c_int, [P, I64, P]),
     "isdfb_grad_buffer": (C.c_int, [P, C.POINTER(P), C.POINTER(I64)]),
     "isdfb_profile_enable": (C.c_int, [P, I32]),
     "isdfb_profile_read": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(I64)]),

@@ -92,6 +92,8 @@ int isdfb_create(const isdfb_model_cfg* cfg, int device, isdfb_ctx** out) {
   CREATE_CUDA(cudaMalloc(&ctx->g_packed, ctx->lay.n_packed * sizeof(float)));
   CREATE_CUDA(cudaMemset(ctx->w_packed, 0, ctx->lay.n_packed * sizeof(float)));
   CREATE_CUDA(cudaMemset(ctx->g_packed, 0, ctx->lay.n_packed * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&ctx->adam_dev, 64));
+  CREATE_CUDA(cudaMemset(ctx->adam_dev, 0, 64));
   if (cfg->precision == ISDFB_PREC_FP32) {
     simt_workspace_floats(ctx->lay, ctx->cap, &ctx->ws_floats);
   } else {
@@ -114,6 +116,7 @@ int isdfb_destroy(isdfb_ctx* ctx) {
   if (ctx->w_packed) cudaFree(ctx->w_packed);
   if (ctx->g_packed) cudaFree(ctx->g_packed);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->adam_dev) cudaFree(ctx->adam_dev);
   delete ctx;
   return ISDFB_OK;
 }
@@ -241,6 +244,18 @@ int isdfb_adamw(isdfb_ctx* ctx, float* params_flat, float* m, float* v, int64_t 
   ENTER(ctx);
   if (!params_flat || !m || !v || step < 1) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_adamw: bad argument");
   return optim_adamw(ctx, params_flat, m, v, step, lr, beta1, beta2, eps, weight_decay, grad_scale, st);
+}
+
+int isdfb_adamw_graph(isdfb_ctx* ctx, float* params_flat, float* m, float* v, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, float grad_scale, void* stream) {
+  ENTER(ctx);
+  if (!params_flat || !m || !v) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_adamw_graph: bad argument");
+  return optim_adamw_dev(ctx, params_flat, m, v, lr, beta1, beta2, eps, weight_decay, grad_scale, st);
+}
+
+int isdfb_adamw_set_step(isdfb_ctx* ctx, int64_t step, void* stream) {
+  ENTER(ctx);
+  return optim_set_step(ctx, step, st);
 }
 
 int isdfb_grad_buffer(isdfb_ctx* ctx, float** ptr, int64_t* n_floats) {

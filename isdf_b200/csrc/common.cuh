@@ -59,6 +59,7 @@ struct isdfb_ctx {
   int64_t ws_floats;
   // tensor-core path workspace -- see tc_chain.cu
   void* tc;                // opaque
+  void* adam_dev;          // device AdamDev {step_size, bc2_sqrt, step} for the graph-safe K6
 };
 
 extern char g_isdfb_create_err[512];
@@ -96,4 +97,7 @@ int simt_pe_encode(isdfb_ctx* ctx, const float* x, int64_t n, float* out, cudaSt
 int optim_pack(isdfb_ctx* ctx, const float* params_flat, cudaStream_t st);
 int optim_adamw(isdfb_ctx* ctx, float* params_flat, float* m, float* v, int64_t step, float lr,
                 float b1, float b2, float eps, float wd, float grad_scale, cudaStream_t st);
+int optim_adamw_dev(isdfb_ctx* ctx, float* params_flat, float* m, float* v, float lr, float b1, float b2,
+                    float eps, float wd, float grad_scale, cudaStream_t st);
+int optim_set_step(isdfb_ctx* ctx, int64_t step, cudaStream_t st);
 int optim_export_grads(isdfb_ctx* ctx, float* grads_flat, cudaStream_t st);

@@ -34,13 +34,26 @@ __global__ void export_grads_kernel(ModelLayout lay, const float* __restrict__ p
   flat[i] = packed[flat_to_packed(lay, i)];
 }
 
+// device-resident step counter + bias corrections, so that K6 can live inside a CUDA graph
+struct AdamDev { float step_size, bc2_sqrt; long long step; };
+
+__global__ void adamw_tick_kernel(AdamDev* st, float lr, float b1, float b2) {
+  const long long t = st->step + 1;
+  st->step = t;
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const double bc2 = 1.0 - pow((double)b2, (double)t);
+  st->step_size = (float)((double)lr / bc1);
+  st->bc2_sqrt = (float)sqrt(bc2);
+}
+
 __global__ void adamw_kernel(ModelLayout lay, float* __restrict__ p, float* __restrict__ m,
                              float* __restrict__ v, const float* __restrict__ g_packed,
                              float* __restrict__ w_packed, float lr_wd_factor, float one_minus_b1,
                              float b2, float one_minus_b2, float step_size, float bc2_sqrt, float eps,
-                             float grad_scale) {
+                             float grad_scale, const AdamDev* __restrict__ dev) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= lay.n_flat) return;
+  if (dev) { step_size = dev->step_size; bc2_sqrt = dev->bc2_sqrt; }
   int64_t j = flat_to_packed(lay, i);
   float g = g_packed[j] * grad_scale;
   float pv = p[i] * lr_wd_factor;                 // param.mul_(1 - lr*wd)
@@ -85,11 +98,37 @@ int optim_adamw(isdfb_ctx* ctx, float* params_flat, float* m, float* v, int64_t 
   float decay = (float)(1.0 - (double)lr * (double)wd);
   adamw_kernel<<<(unsigned)((lay.n_flat + 255) / 256), 256, 0, st>>>(
       lay, params_flat, m, v, ctx->g_packed, ctx->w_packed, decay, (float)(1.0 - (double)b1), b2,
-      (float)(1.0 - (double)b2), step_size, bc2_sqrt, eps, grad_scale);
+      (float)(1.0 - (double)b2), step_size, bc2_sqrt, eps, grad_scale, nullptr);
   ISDFB_LAUNCHED(ctx);
   ISDFB_CUDA_OK(ctx, cudaGetLastError());
   int rc = tc_repack(ctx, st);
   if (rc) return rc;
   ctx->weights_ready = true;
+  return ISDFB_OK;
+}
+
+// graph-safe variant: the step counter lives on the device (ctx->adam_dev) and is advanced by a 1-thread kernel
+int optim_adamw_dev(isdfb_ctx* ctx, float* params_flat, float* m, float* v, float lr, float b1, float b2,
+                    float eps, float wd, float grad_scale, cudaStream_t st) {
+  const ModelLayout& lay = ctx->lay;
+  AdamDev* dev = reinterpret_cast<AdamDev*>(ctx->adam_dev);
+  adamw_tick_kernel<<<1, 1, 0, st>>>(dev, lr, b1, b2);
+  ISDFB_LAUNCHED(ctx);
+  float decay = (float)(1.0 - (double)lr * (double)wd);
+  adamw_kernel<<<(unsigned)((lay.n_flat + 255) / 256), 256, 0, st>>>(
+      lay, params_flat, m, v, ctx->g_packed, ctx->w_packed, decay, (float)(1.0 - (double)b1), b2,
+      (float)(1.0 - (double)b2), 0.f, 1.f, eps, grad_scale, dev);
+  ISDFB_LAUNCHED(ctx);
+  ISDFB_CUDA_OK(ctx, cudaGetLastError());
+  int rc = tc_repack(ctx, st);
+  if (rc) return rc;
+  ctx->weights_ready = true;
+  return ISDFB_OK;
+}
+
+int optim_set_step(isdfb_ctx* ctx, int64_t step, cudaStream_t st) {
+  AdamDev h = {0.f, 1.f, (long long)step};
+  ISDFB_CUDA_OK(ctx, cudaMemcpyAsync(ctx->adam_dev, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  ISDFB_CUDA_OK(ctx, cudaStreamSynchronize(st));
   return ISDFB_OK;
 }

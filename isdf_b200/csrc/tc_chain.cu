@@ -594,13 +594,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
 
 int tc_chain_launch(isdfb_ctx* ctx, const TcChainArgs& args, int passes, int grid, cudaStream_t st) {
   if (passes == 3) {
-    ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
     tc_chain_kernel<3><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
   } else {
-    ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
     tc_chain_kernel<1><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
   }
   ISDFB_LAUNCHED(ctx);
   ISDFB_CUDA_OK(ctx, cudaGetLastError());
+  return ISDFB_OK;
+}
+
+int tc_chain_init(isdfb_ctx* ctx) {
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
   return ISDFB_OK;
 }

@@ -161,13 +161,17 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const TcDwArgs arg
 
 int tc_dw_launch(isdfb_ctx* ctx, const TcDwArgs& args, int passes, int grid, cudaStream_t st) {
   if (passes == 3) {
-    ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_dw_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<3>::kSmem));
     tc_dw_kernel<3><<<grid, DW_THREADS, DwCfg<3>::kSmem, st>>>(args);
   } else {
-    ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_dw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<1>::kSmem));
     tc_dw_kernel<1><<<grid, DW_THREADS, DwCfg<1>::kSmem, st>>>(args);
   }
   ISDFB_LAUNCHED(ctx);
   ISDFB_CUDA_OK(ctx, cudaGetLastError());
+  return ISDFB_OK;
+}
+
+int tc_dw_init(isdfb_ctx* ctx) {
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_dw_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<3>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_dw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<1>::kSmem));
   return ISDFB_OK;
 }

@@ -40,12 +40,16 @@ void tc_destroy(isdfb_ctx* ctx) {
   ctx->tc = nullptr;
 }
 
+int tc_chain_init(isdfb_ctx* ctx);
+int tc_dw_init(isdfb_ctx* ctx);
+
 int tc_create(isdfb_ctx* ctx) {
   const ModelLayout& lay = ctx->lay;
   if (lay.H != TC_H || lay.Ep != TC_H)
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG,
                "tensor-core path supports hidden=256 and embedding <= 256 (n_freqs <= 6); got hidden=%d E=%d. "
                "Use precision fp32 for other shapes.", lay.H, lay.E);
+  { int rc = tc_chain_init(ctx); if (rc) return rc; rc = tc_dw_init(ctx); if (rc) return rc; }
   TcState* tc = new (std::nothrow) TcState();
   if (!tc) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "out of host memory");
   memset(tc, 0, sizeof(*tc));

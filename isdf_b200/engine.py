@@ -230,6 +230,15 @@ class Engine:
                                       self._stream()))
 
 
+    def adamw_graph(self, params, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):
+        """K6 with the step counter on the device (CUDA-graph capturable)."""
+        self._ck(self.lib.isdfb_adamw_graph(self._ctx, _ptr(params), _ptr(m), _ptr(v), float(lr), float(beta1),
+                                            float(beta2), float(eps), float(weight_decay), float(grad_scale),
+                                            self._stream()))
+
+    def adamw_set_step(self, step):
+        self._ck(self.lib.isdfb_adamw_set_step(self._ctx, int(step), self._stream()))
+
     # ---- kernel timing -------------------------------------------------
     def profile(self, enable):
         self._ck(self.lib.isdfb_profile_enable(self._ctx, 1 if enable else 0))

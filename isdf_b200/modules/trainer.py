@@ -46,6 +46,7 @@ class FusedAdamW:
         self.step_count = 0
         self.exp_avg = None
         self.exp_avg_sq = None
+        self._dev_step_engine = None
 
     def _state(self):
         flat = self.sdf_map.flat_parameters()
@@ -55,12 +56,16 @@ class FusedAdamW:
         return flat
 
     def step(self, grad_scale=1.0):
+        """K6 with the step counter on the device, so the call can be captured in a CUDA graph."""
         eng = self.sdf_map.engine()
         flat = self._state()
         g = self.param_groups[0]
+        if self._dev_step_engine is not eng:          # (re)align the device counter with the host count
+            eng.adamw_set_step(self.step_count)
+            self._dev_step_engine = eng
         self.step_count += 1
-        eng.adamw(flat, self.exp_avg, self.exp_avg_sq, self.step_count, g["lr"], g["betas"][0], g["betas"][1],
-                  g["eps"], g["weight_decay"], grad_scale)
+        eng.adamw_graph(flat, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                        g["weight_decay"], grad_scale)
         self.sdf_map.mark_packed()
 
     def zero_grad(self, set_to_none=True):
@@ -90,6 +95,7 @@ class FusedAdamW:
                 self.exp_avg_sq[off:off + n] = st["exp_avg_sq"].reshape(-1).to(self.exp_avg.device)
                 self.step_count = int(float(st["step"]))
             off += n
+        self._dev_step_engine = None
 
 
 class Trainer:
@@ -119,6 +125,9 @@ class Trainer:
         self.rng_device = rng_device            # e.g. 'cpu' to replay a CPU run of the reference
         self.fix_normal_window = bool(b200.get("fix_normal_window", 0))
         self.max_points = int(b200.get("max_points", 32768))
+        self.use_graph = bool(b200.get("cuda_graph", 1))
+        self._graph = None
+        self._graph_seen = None
         self.dist_world, self.dist_rank = 1, 0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.dist_world, self.dist_rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
@@ -375,9 +384,10 @@ class Trainer:
         w = self.frames.frame_avg_losses[:-2]
         w = w + (w.sum() <= 0)                 # all-zero history -> uniform (the reference would divide 0/0)
         if self.rng_mode == "fast":
-            pick = torch.multinomial(w / w.sum(), self.window_size - 2, replacement=False)
-            last = torch.tensor([n - 2, n - 1], device=pick.device)
-            return torch.cat([pick, last])
+            # Gumbel top-k == sequential sampling without replacement with p ~ w (Plackett-Luce); sync-free
+            keys = torch.log(w.clamp_min(1e-30)) - torch.log(-torch.log(torch.rand_like(w).clamp_min(1e-30)))
+            pick = keys.topk(self.window_size - 2).indices
+            return torch.cat([pick, torch.arange(n - 2, n, device=pick.device)])
         p = (w / w.sum()).cpu().numpy()
         rand_ints = np.random.choice(np.arange(0, limit), size=self.window_size - 2, replace=False, p=p)
         return [*rand_ints, n - 2, n - 1]
@@ -483,18 +493,18 @@ class Trainer:
         return total_loss, losses, loss_approx, frame_avg_loss
 
     # ---- one optimisation step (trainer.py:951-1016) -----------------------------------------
-    def step(self, sync=True):
-        if sync:
-            start, end = start_timing()
+    def _step_body(self):
         depth_batch = self.frames.depth_batch
         T_WC_batch = self.frames.T_WC_batch
         norm_batch = self.frames.normal_batch if self.do_normal else None
         if len(self.frames) > self.window_size and self.incremental:
             idxs = self.select_keyframes()
+        elif self.rng_mode == "fast":
+            idxs = torch.arange(T_WC_batch.shape[0], device=self.device)
         else:
             idxs = np.arange(T_WC_batch.shape[0])
         self.active_idxs = idxs
-        idx_t = torch.as_tensor(idxs, device=self.device, dtype=torch.int64)
+        idx_t = idxs if torch.is_tensor(idxs) else torch.as_tensor(idxs, device=self.device, dtype=torch.int64)
         sample_pts = self.sample_points(depth_batch, T_WC_batch, norm_batch=norm_batch, frame_map=idx_t)
         self.active_pixels = {k: sample_pts[k] for k in ("indices_b", "indices_h", "indices_w")}
         total_loss, losses, active_loss_approx, frame_avg_loss = self.sdf_eval_and_loss(sample_pts, do_avg_loss=True)
@@ -504,6 +514,41 @@ class Trainer:
             torch.distributed.all_reduce(self.sdf_map.engine().grad_buffer())
             scale = 1.0 / self.dist_world
         self.optimiser.step(grad_scale=scale)
+        return losses
+
+    def _graph_key(self):
+        f = self.frames
+        return (len(f), f.depth_batch.data_ptr(), f.T_WC_batch.data_ptr(),
+                f.normal_batch.data_ptr() if f.normal_batch is not None else 0, f.frame_avg_losses.data_ptr(),
+                self.noise_std, self.sdf_map.flat_parameters().data_ptr())
+
+    def _step_graphed(self):
+        """fast mode: the whole step (RNG, K1, K4, K5, C1, K6) as ONE CUDA-graph launch.  The graph is
+        re-captured whenever the keyframe buffer changes shape or address (a new keyframe)."""
+        key = self._graph_key()
+        g = self._graph
+        if g is not None and g[0] == key:
+            g[1].replay()
+            return g[2]
+        if self._graph_seen != key:                 # first step with this buffer layout runs eagerly
+            self._graph_seen = key
+            self._graph = None
+            return self._step_body()
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(graph):
+            losses = self._step_body()
+        graph.replay()                              # capture does not execute
+        self._graph = (key, graph, losses)
+        return losses
+
+    def step(self, sync=True):
+        if sync:
+            start, end = start_timing()
+        if self.use_graph and self.rng_mode == "fast":
+            losses = self._step_graphed()
+        else:
+            losses = self._step_body()
         step_time = end_timing(start, end) if sync else 0.0
         self.tot_step_time += (1 / self.frac_time_perception) * (step_time / 1000.)
         self.steps_since_frame += 1
