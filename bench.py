@@ -164,14 +164,26 @@ def main():
         run_reference_arm(args, wl, rank)
         return
 
+    verbose = bool(os.environ.get("ISDFB_BENCH_VERBOSE"))
+
+    def say(msg):
+        if verbose:
+            sys.stderr.write("[bench rank %d] %s\n" % (rank, msg))
+            sys.stderr.flush()
+
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    say("process group ready")
     import __graft_entry__ as ge
-    ge.build()
+    if rank == 0:
+        ge.build()
+    if dist is not None:
+        dist.barrier()
+    say("library built")
     from isdf.modules import trainer as trainer_mod
     import numpy as np
 
@@ -185,6 +197,7 @@ def main():
     for i in range(wl["keyframes"]):
         tr.last_is_keyframe = True
         tr.add_data(tr.get_data([rank + i * world]))
+    say("keyframes resident")
     S = wl["n_strat"] + wl["n_surf"]
     rays_per_step = wl["n_rays"] * 5
     pts_per_step = rays_per_step * S
@@ -203,10 +216,12 @@ def main():
     tr.step(sync=False)
     launches_per_step = eng.launches - l0
     tr.use_graph = True
+    say("eager steps ok, %d launches/step" % launches_per_step)
     # ---------------- device-resident throughput (`value`) ----------------
     for _ in range(max(args.warmup, 3)):
         tr.step(sync=False)
     barrier()
+    say("warm-up done")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -226,6 +241,7 @@ def main():
     ms_max = float(t.item())
     value = world * pts_per_step * args.steps / (ms_max / 1000.0)
 
+    say("timed loop done: %.3f ms/step" % (ms_max / args.steps))
     # ---------------- end-to-end through the public API (`e2e`) ----------------
     # driver pattern of train.py:102-136: a new host frame is ingested every iters_per_frame steps
     # (pinned H2D of image+depth+pose, normals on device), every step's loss is read back (D2H).
@@ -250,6 +266,7 @@ def main():
     e2e_ms = float(t.item())
     e2e_val = world * pts_per_step * args.steps / (e2e_ms / 1000.0)
 
+    say("e2e loop done")
     # ---------------- roofline of the dominant kernel (rank 0, events inside the library) -------------
     roof = None
     peaks = load_peaks()

@@ -29,6 +29,7 @@ from ..datasets.data_util import FrameData
 from ..engine import make_camera, make_loss_cfg
 from ..eval.metrics import start_timing, end_timing
 from ..geometry import transform
+from .. import parallel
 from . import embedding, fc_map, render, sample
 
 _OUT_OF_SCOPE = ("view_sdf", "latest_frame_vis", "update_vis_vars", "frames_vis", "draw_3D", "draw_obj_3D",
@@ -128,9 +129,7 @@ class Trainer:
         self.use_graph = bool(b200.get("cuda_graph", 1))
         self._graph = None
         self._graph_seen = None
-        self.dist_world, self.dist_rank = 1, 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.dist_world, self.dist_rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        self.dist_world, self.dist_rank = parallel.world()
 
         self.frames = FrameData()
         self.set_params()
@@ -493,7 +492,8 @@ class Trainer:
         return total_loss, losses, loss_approx, frame_avg_loss
 
     # ---- one optimisation step (trainer.py:951-1016) -----------------------------------------
-    def _step_body(self):
+    def _step_front(self):
+        """Everything up to and including the fused forward/backward (gradient left in the engine)."""
         depth_batch = self.frames.depth_batch
         T_WC_batch = self.frames.T_WC_batch
         norm_batch = self.frames.normal_batch if self.do_normal else None
@@ -509,11 +509,17 @@ class Trainer:
         self.active_pixels = {k: sample_pts[k] for k in ("indices_b", "indices_h", "indices_w")}
         total_loss, losses, active_loss_approx, frame_avg_loss = self.sdf_eval_and_loss(sample_pts, do_avg_loss=True)
         self.frames.frame_avg_losses[idx_t] = frame_avg_loss
-        scale = 1.0
-        if self.dist_world > 1:                                   # C1: the only collective
-            torch.distributed.all_reduce(self.sdf_map.engine().grad_buffer())
-            scale = 1.0 / self.dist_world
-        self.optimiser.step(grad_scale=scale)
+        return losses
+
+    def _allreduce(self):
+        """C1: the only collective -- sum of the packed gradient over the data-parallel ranks."""
+        if self.dist_world > 1:
+            parallel.allreduce_sum_(self.sdf_map.engine().grad_buffer())
+
+    def _step_body(self):
+        losses = self._step_front()
+        self._allreduce()
+        self.optimiser.step(grad_scale=1.0 / self.dist_world)
         return losses
 
     def _graph_key(self):
@@ -523,23 +529,37 @@ class Trainer:
                 self.noise_std, self.sdf_map.flat_parameters().data_ptr())
 
     def _step_graphed(self):
-        """fast mode: the whole step (RNG, K1, K4, K5, C1, K6) as ONE CUDA-graph launch.  The graph is
-        re-captured whenever the keyframe buffer changes shape or address (a new keyframe)."""
+        """fast mode: the step as CUDA-graph launches -- one graph on a single GPU; with data parallelism
+        two graphs (RNG+K1+K4+K5 | K6) around the eager NCCL all-reduce.  Re-captured whenever the keyframe
+        buffer changes shape or address (a new keyframe)."""
         key = self._graph_key()
         g = self._graph
         if g is not None and g[0] == key:
             g[1].replay()
+            if g[3] is not None:
+                self._allreduce()
+                g[3].replay()
             return g[2]
         if self._graph_seen != key:                 # first step with this buffer layout runs eagerly
             self._graph_seen = key
             self._graph = None
             return self._step_body()
-        graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize(self.device)
-        with torch.cuda.graph(graph):
-            losses = self._step_body()
-        graph.replay()                              # capture does not execute
-        self._graph = (key, graph, losses)
+        front, back = torch.cuda.CUDAGraph(), None
+        if self.dist_world == 1:
+            with torch.cuda.graph(front):
+                losses = self._step_body()
+            front.replay()                          # capture does not execute
+        else:
+            with torch.cuda.graph(front):
+                losses = self._step_front()
+            front.replay()
+            self._allreduce()
+            back = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(back):
+                self.optimiser.step(grad_scale=1.0 / self.dist_world)
+            back.replay()
+        self._graph = (key, front, losses, back)
         return losses
 
     def step(self, sync=True):
