@@ -113,6 +113,13 @@ int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC /*[F,4,4]*/, const int64
                       float* pc /*[R,S,3]*/, float* z_vals /*[R,S]*/, float* dirs_C /*[R,3]*/,
                       float* T_WC_sample /*[R,4,4]*/, void* stream);
 
+/* ---- N3: frame ingest (row "next" of SURVEY.md 8f) -------------------------------------------
+ * Per-pixel normals of one depth image [H,W] -> normals [H,W,3]; fuses
+ * transform.pointcloud_from_depth_torch + estimate_pointcloud_normals (transform.py:169-196, 215-270;
+ * called once per new frame from Trainer.get_data, trainer.py:553-557).  NaN where undefined.        */
+int isdfb_ingest_normals(isdfb_ctx* ctx, const float* depth, const isdfb_camera* cam, float* normals,
+                         void* stream);
+
 /* ---- positional encoding alone -----------------------------------------------------------
  * PostionalEncoding.forward (embedding.py:95-111): out[n, E] row-major.  The training and
  * inference kernels never materialise this tensor; the entry exists for API parity.        */

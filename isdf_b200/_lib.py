@@ -49,6 +49,7 @@ SIGNATURES = {
     "isdfb_gather_rays": (C.c_int, [P, P, P, P, I32, P, P, P, I64, C.POINTER(Camera), P, P, P, P]),
     "isdfb_sample_rays": (C.c_int, [P, P, P, P, P, P, P, P, P, P, P, P, I64, I32, I32, C.POINTER(Camera), F, F,
                                     P, P, P, P, P]),
+    "isdfb_ingest_normals": (C.c_int, [P, P, C.POINTER(Camera), P, P]),
     "isdfb_pe_encode": (C.c_int, [P, P, I64, P, P]),
     "isdfb_mlp_forward": (C.c_int, [P, P, P, F, I64, P, P]),
     "isdfb_mlp_forward_grad": (C.c_int, [P, P, P, F, I64, P, P, P]),

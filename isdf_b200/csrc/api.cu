@@ -11,6 +11,7 @@ int sample_along(isdfb_ctx*, const float*, const int64_t*, const int64_t*, const
                  const isdfb_camera*, float, float, float*, float*, float*, float*, cudaStream_t);
 int sample_frame_bins(isdfb_ctx*, float*, const float*, const uint8_t*, const int64_t*, const int64_t*,
                       const int64_t*, int64_t, int, int, int, int, int, float*, float*, cudaStream_t);
+int sample_ingest_normals(isdfb_ctx*, const float*, const isdfb_camera*, float*, cudaStream_t);
 int tc_create(isdfb_ctx* ctx);
 void tc_destroy(isdfb_ctx* ctx);
 int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n,
@@ -162,6 +163,12 @@ int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC, const int64_t* frame_ma
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_rays: bad sample counts (n_strat %d n_surf %d)", n_strat, n_surf);
   return sample_along(ctx, T_WC, frame_map, ib, ih, iw, dirs_C_in, depth_sample, far, u_strat, n_near, lin, n_rays, n_strat,
                       n_surf, cam, min_depth, dist_behind, pc, z_vals, dirs_C, T_WC_sample, st);
+}
+
+int isdfb_ingest_normals(isdfb_ctx* ctx, const float* depth, const isdfb_camera* cam, float* normals, void* stream) {
+  ENTER(ctx);
+  if (!depth || !cam || !normals) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_ingest_normals: null argument");
+  return sample_ingest_normals(ctx, depth, cam, normals, st);
 }
 
 int isdfb_pe_encode(isdfb_ctx* ctx, const float* x, int64_t n, float* out, void* stream) {

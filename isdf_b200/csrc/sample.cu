@@ -90,23 +90,39 @@ __global__ void sample_rays_kernel(const float* __restrict__ T_WC, const int64_t
 // Rays are ordered by frame (sample.py:18-19 builds indices_b with repeat_interleave and the
 // compaction keeps order).  A ray is "live" unless a LATER ray hits the same pixel of the same
 // frame (CPU index_put: last writer wins; the mask counts the pixel once).
+// one warp per ray: the 32 lanes scan the later rays of the same frame for a duplicate pixel and add up
+// the ray's samples; lane 0 commits.
 __global__ void frame_bins_accum_kernel(const float* __restrict__ loss_mat, const uint8_t* __restrict__ ray_valid,
                                         const int64_t* __restrict__ ib, const int64_t* __restrict__ ih,
                                         const int64_t* __restrict__ iw, int64_t n_rays, int S, int H, int W,
                                         int factor, float* __restrict__ bins, float* __restrict__ cnt) {
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (r >= n_rays) return;
   if (ray_valid && !ray_valid[r]) return;
-  int64_t b = ib[r], h = ih[r], w = iw[r];
-  for (int64_t q = r + 1; q < n_rays && ib[q] == b; ++q) {
-    if (ih[q] == h && iw[q] == w && (!ray_valid || ray_valid[q])) return;   // shadowed
+  const int64_t b = ib[r], h = ih[r], w = iw[r];
+  bool shadowed = false;
+  for (int64_t q0 = r + 1; q0 < n_rays; q0 += 32) {
+    const int64_t q = q0 + lane;
+    bool same_frame = false, hit = false;
+    if (q < n_rays) {
+      same_frame = ib[q] == b;
+      hit = same_frame && ih[q] == h && iw[q] == w && (!ray_valid || ray_valid[q]);
+    }
+    if (__any_sync(0xffffffffu, hit)) { shadowed = true; break; }
+    if (!__all_sync(0xffffffffu, same_frame)) break;          // rays are ordered by frame
   }
+  if (shadowed) return;
   float s = 0.f;
-  for (int j = 0; j < S; ++j) s += loss_mat[r * S + j];
-  int by = (int)(h / (H / factor)), bx = (int)(w / (W / factor));
-  int64_t cell = (b * factor + by) * factor + bx;
-  atomicAdd(bins + cell, s);
-  atomicAdd(cnt + cell, 1.0f);
+  for (int j = lane; j < S; j += 32) s += loss_mat[r * S + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const int by = (int)(h / (H / factor)), bx = (int)(w / (W / factor));
+    const int64_t cell = (b * factor + by) * factor + bx;
+    atomicAdd(bins + cell, s);
+    atomicAdd(cnt + cell, 1.0f);
+  }
 }
 
 __global__ void frame_bins_final_kernel(const float* __restrict__ bins, const float* __restrict__ cnt,
@@ -131,6 +147,67 @@ __global__ void frame_bins_final_kernel(const float* __restrict__ bins, const fl
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     frame_avg[f] = t / (float)cells;
   }
+}
+
+// ---- N3: frame ingest ------------------------------------------------------------------------
+// Per-pixel surface normals of a depth image (reference transform.py:169-196 + 215-270): back-project
+// p = (z (c-cx)/fx, z (r-cy)/fy, z); among the 8 neighbour pairs (k, k+2) at pixel distance 2 pick the
+// one minimising |p_k - p| + |p_{k+2} - p| (out-of-image = NaN = infinite cost, first minimum wins) and
+// return the normalised cross product.  One thread per pixel; 16 fused temporaries instead of HBM tensors.
+__global__ void ingest_normals_kernel(const float* __restrict__ depth, isdfb_camera cam, float* __restrict__ normals) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= cam.W || r >= cam.H) return;
+  const int offs[8][2] = {{-2, 0}, {-2, 2}, {0, 2}, {2, 2}, {2, 0}, {2, -2}, {0, -2}, {-2, -2}};   // (dy, dx)
+  auto point = [&](int rr, int cc, float* o) {
+    const float z = depth[(size_t)rr * cam.W + cc];
+    o[0] = z * ((float)cc - cam.cx) / cam.fx;
+    o[1] = z * ((float)rr - cam.cy) / cam.fy;
+    o[2] = z;
+  };
+  float p[3];
+  point(r, c, p);
+  float dv[8][3], len[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int rr = r + offs[k][0], cc = c + offs[k][1];
+    if (rr < 0 || rr >= cam.H || cc < 0 || cc >= cam.W) {
+      dv[k][0] = dv[k][1] = dv[k][2] = __int_as_float(0x7fc00000);
+      len[k] = __int_as_float(0x7f800000);
+    } else {
+      float q[3];
+      point(rr, cc, q);
+      dv[k][0] = q[0] - p[0]; dv[k][1] = q[1] - p[1]; dv[k][2] = q[2] - p[2];
+      len[k] = sqrtf(dv[k][0] * dv[k][0] + dv[k][1] * dv[k][1] + dv[k][2] * dv[k][2]);
+      if (isnan(len[k])) len[k] = __int_as_float(0x7f800000);
+    }
+  }
+  int best = 0;
+  float bc = len[0] + len[2];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    const float cst = len[k] + len[(k + 2) & 7];
+    if (cst < bc) { bc = cst; best = k; }
+  }
+  float a[3], b[3];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k == best) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t) { a[t] = dv[k][t]; b[t] = dv[(k + 2) & 7][t]; }
+    }
+  const float nx = a[1] * b[2] - a[2] * b[1], ny = a[2] * b[0] - a[0] * b[2], nz = a[0] * b[1] - a[1] * b[0];
+  const float inv = 1.f / sqrtf(nx * nx + ny * ny + nz * nz);
+  float* o = normals + ((size_t)r * cam.W + c) * 3;
+  o[0] = nx * inv; o[1] = ny * inv; o[2] = nz * inv;
+}
+
+int sample_ingest_normals(isdfb_ctx* ctx, const float* depth, const isdfb_camera* cam, float* normals, cudaStream_t st) {
+  dim3 blk(32, 8), grd((cam->W + 31) / 32, (cam->H + 7) / 8);
+  ingest_normals_kernel<<<grd, blk, 0, st>>>(depth, *cam, normals);
+  ISDFB_LAUNCHED(ctx);
+  ISDFB_CUDA_OK(ctx, cudaGetLastError());
+  return ISDFB_OK;
 }
 
 int sample_gather(isdfb_ctx* ctx, const float* depth, const float* normals, const int64_t* frame_map,
@@ -170,7 +247,7 @@ int sample_frame_bins(isdfb_ctx* ctx, float* scratch, const float* loss_mat, con
   float* cnt = scratch + cells;
   ISDFB_CUDA_OK(ctx, cudaMemsetAsync(scratch, 0, 2 * (size_t)cells * sizeof(float), st));
   if (n_rays > 0) {
-    frame_bins_accum_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, st>>>(
+    frame_bins_accum_kernel<<<(unsigned)((n_rays * 32 + 255) / 256), 256, 0, st>>>(
         loss_mat, ray_valid, ib, ih, iw, n_rays, S, H, W, factor, bins, cnt);
     ISDFB_LAUNCHED(ctx);
   }

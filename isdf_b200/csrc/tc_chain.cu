@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
     if (elect_one()) {
       uint32_t j = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
+        const int tile = args.tile0 + blockIdx.x + it * gridDim.x;
         for (int s = 0; s < n_steps; ++s) {
           const TcStep st = args.steps[s];
           if (args.prefetch && s + 1 < n_steps) {
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
     float lsum0 = 0.f, lsum1 = 0.f, lsum2 = 0.f, lsum3 = 0.f, sbsum = 0.f;
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
+      const int tile = args.tile0 + blockIdx.x + it * gridDim.x;
       const int64_t pl = (int64_t)tile * TC_TILE + p;             // point index inside the chunk
       const bool real = pl < args.n_points;
       EpiT T;

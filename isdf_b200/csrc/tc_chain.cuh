@@ -17,7 +17,8 @@ struct TcStep {
 struct TcChainArgs {
   TcStep steps[TC_MAX_STEPS];
   int32_t n_steps, mode, L, ic, E, S;
-  int32_t n_tiles;
+  int32_t n_tiles;           // tiles processed by this launch ...
+  int32_t tile0;             // ... starting at this tile of the chunk
   int32_t prefetch;          // 1: bulk-prefetch the next step's side arrays into L2 (producer warp)
   int64_t n_points;          // real points in this chunk
   int64_t p0;                // global index of the chunk's first point (sample index r*S+j)

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const TcDwArgs arg
     if (elect_one()) {
       uint32_t j = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const size_t tile_off = (size_t)(split + it * n_splits) * TC_DWL_TILE_BYTES;
+        const size_t tile_off = (size_t)(args.tile0 + split + it * n_splits) * TC_DWL_TILE_BYTES;
         for (int pi = 0; pi < job.n_pairs; ++pi) {
           const TcDwPair pr = job.pair[pi];
           const size_t xo = (size_t)pr.x_arr * args.dwl_stride + tile_off + (size_t)job.half * 4096;

@@ -33,6 +33,9 @@ void tc_destroy(isdfb_ctx* ctx) {
   if (tc->dwl_hi) cudaFree(tc->dwl_hi);
   if (tc->dwl_lo) cudaFree(tc->dwl_lo);
   if (tc->sig16) cudaFree(tc->sig16);
+  if (tc->side) cudaStreamDestroy(tc->side);
+  if (tc->ev_fork) cudaEventDestroy(tc->ev_fork);
+  if (tc->ev_join) cudaEventDestroy(tc->ev_join);
   for (int i = 0; i < TC_PROF_MAX; ++i)
     for (int k = 0; k < 3; ++k)
       if (tc->ev[i][k]) cudaEventDestroy(tc->ev[i][k]);
@@ -56,6 +59,9 @@ int tc_create(isdfb_ctx* ctx) {
   ctx->tc = tc;
   const int L = lay.L, ic = lay.block + 1;
   ISDFB_CUDA_OK(ctx, cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  ISDFB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&tc->side, cudaStreamNonBlocking));
+  ISDFB_CUDA_OK(ctx, cudaEventCreateWithFlags(&tc->ev_fork, cudaEventDisableTiming));
+  ISDFB_CUDA_OK(ctx, cudaEventCreateWithFlags(&tc->ev_join, cudaEventDisableTiming));
   tc->n_units = L + 1;
   for (int l = 0; l < L; ++l) { tc->units.u[l].w_off = lay.layer[l].w_off; tc->units.u[l].ld = lay.layer[l].k0; }
   tc->units.u[L].w_off = lay.layer[ic].we_off;
@@ -198,16 +204,39 @@ int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* 
     a.ray_valid = ray_valid;
     a.loss_mat = loss_mat;
     a.loss_sums = loss_sums;
-    const int grid = a.n_tiles < tc->num_sms ? a.n_tiles : tc->num_sms;
+    const int total_tiles = a.n_tiles;
     const int pi = prof_begin(tc, st);
-    int rc = tc_chain_launch(ctx, a, passes_of(ctx), grid, st);
-    if (rc) return rc;
-    prof_mark(tc, pi, 1, st);
     TcDwArgs d = tc->dw;
-    d.n_tiles = a.n_tiles;
-    rc = tc_dw_launch(ctx, d, passes_of(ctx), tc->num_sms, st);
-    if (rc) return rc;
-    prof_mark(tc, pi, 2, st);
+    int rc;
+    if (total_tiles > tc->num_sms && total_tiles < 2 * tc->num_sms && !tc->profiling && !getenv("ISDFB_NO_OVERLAP")) {
+      // two waves: the weight gradients of wave 1 run on a side stream underneath the (partial) wave 2
+      a.tile0 = 0; a.n_tiles = tc->num_sms;
+      rc = tc_chain_launch(ctx, a, passes_of(ctx), tc->num_sms, st);
+      if (rc) return rc;
+      ISDFB_CUDA_OK(ctx, cudaEventRecord(tc->ev_fork, st));
+      ISDFB_CUDA_OK(ctx, cudaStreamWaitEvent(tc->side, tc->ev_fork, 0));
+      d.tile0 = 0; d.n_tiles = tc->num_sms;
+      const int rest = total_tiles - tc->num_sms;
+      rc = tc_dw_launch(ctx, d, passes_of(ctx), tc->num_sms - rest > 14 ? tc->num_sms - rest : 14, tc->side);
+      if (rc) return rc;
+      ISDFB_CUDA_OK(ctx, cudaEventRecord(tc->ev_join, tc->side));
+      a.tile0 = tc->num_sms; a.n_tiles = rest;
+      rc = tc_chain_launch(ctx, a, passes_of(ctx), rest, st);
+      if (rc) return rc;
+      ISDFB_CUDA_OK(ctx, cudaStreamWaitEvent(st, tc->ev_join, 0));
+      d.tile0 = tc->num_sms; d.n_tiles = rest;
+      rc = tc_dw_launch(ctx, d, passes_of(ctx), tc->num_sms, st);
+      if (rc) return rc;
+    } else {
+      const int grid = a.n_tiles < tc->num_sms ? a.n_tiles : tc->num_sms;
+      rc = tc_chain_launch(ctx, a, passes_of(ctx), grid, st);
+      if (rc) return rc;
+      prof_mark(tc, pi, 1, st);
+      d.tile0 = 0; d.n_tiles = total_tiles;
+      rc = tc_dw_launch(ctx, d, passes_of(ctx), tc->num_sms, st);
+      if (rc) return rc;
+      prof_mark(tc, pi, 2, st);
+    }
   }
   return ISDFB_OK;
 }

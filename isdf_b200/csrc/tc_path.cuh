@@ -19,7 +19,7 @@ struct TcDwJob {
 
 struct TcDwArgs {
   TcDwJob jobs[TC_MAX_JOBS];
-  int32_t n_jobs, n_tiles;
+  int32_t n_jobs, n_tiles, tile0;
   const uint8_t *dwl_hi, *dwl_lo;
   size_t dwl_stride;
   float* g_packed;
@@ -43,6 +43,8 @@ struct TcState {
   cudaEvent_t ev[TC_PROF_MAX][3];   // before chain, after chain, after dW
   int ev_kind[TC_PROF_MAX];         // 1: chain only, 2: chain + dW
   int n_ev;
+  cudaStream_t side;       // second stream: weight gradients of the first wave overlap the second wave
+  cudaEvent_t ev_fork, ev_join;
   long long* dbg_clock;    // device buffer [128] when ISDFB_DEBUG_CLOCK is set
 };
 

@@ -19,6 +19,8 @@ class SyntheticStream:
         u = np.arange(W, dtype=np.float32)[None, :]
         self._v_term = (0.3 * np.cos(v / 60.0)).astype(np.float32)
         self._u = u
+        self.cache_frames = False          # True: keep generated host frames (they stand in for decoded images)
+        self._cache = {}
 
     def __len__(self):
         return self.n_frames
@@ -41,8 +43,13 @@ class SyntheticStream:
 
     def __getitem__(self, k):
         k = int(k) % self.n_frames
+        if k in self._cache:
+            return self._cache[k]
         image = np.full((self.H, self.W, 3), 128, dtype=np.uint8)
-        return {"image": image, "depth": self.depth(k), "T": self.pose(k)}
+        item = {"image": image, "depth": self.depth(k), "T": self.pose(k)}
+        if self.cache_frames:
+            self._cache[k] = item
+        return item
 
 
 class ReplicaDataset:

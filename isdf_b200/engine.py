@@ -137,6 +137,12 @@ class Engine:
                                             self._stream()))
         return pc, z, dirs_C, T_s
 
+    def ingest_normals(self, depth, cam):
+        depth = _f32(depth, "depth", self.device)
+        out = torch.empty(*depth.shape, 3, dtype=torch.float32, device=self.device)
+        self._ck(self.lib.isdfb_ingest_normals(self._ctx, _ptr(depth), C.byref(cam), _ptr(out), self._stream()))
+        return out
+
     def pe_encode(self, x):
         x = _f32(x, "x", self.device)
         n = x.numel() // 3

@@ -129,6 +129,7 @@ class Trainer:
         self.use_graph = bool(b200.get("cuda_graph", 1))
         self._graph = None
         self._graph_seen = None
+        self._stage = None
         self.dist_world, self.dist_rank = parallel.world()
 
         self.frames = FrameData()
@@ -311,19 +312,40 @@ class Trainer:
             self.add_data(self.get_data(self.indices))
 
     def get_data(self, idxs):
-        """Host frames -> device FrameData (+ per-pixel normals when the normal loss is on)."""
+        """Host frames -> device FrameData (+ per-pixel normals when the normal loss is on).
+        reference mode: the reference's torch op sequence for the normals (bit-comparable);
+        fast mode: pinned staging buffer + the fused N3 kernel, and the RGB image stays on the host
+        (it is only read by visualisation code)."""
         out = FrameData()
+        fast = self.rng_mode == "fast"
         for idx in idxs:
             s = self.scene_dataset[idx]
             im_np, depth_np, T_np = s["image"][None, ...], s["depth"][None, ...], s["T"][None, ...]
-            depth = torch.from_numpy(np.ascontiguousarray(depth_np)).float().pin_memory().to(self.device, non_blocking=True)
-            T = torch.from_numpy(np.ascontiguousarray(T_np)).float().pin_memory().to(self.device, non_blocking=True)
-            im = torch.from_numpy(np.ascontiguousarray(im_np)).to(self.device).float() / 255.
+            if fast:
+                if self._stage is None:
+                    self._stage = (torch.empty(1, self.H, self.W, dtype=torch.float32).pin_memory(),
+                                   torch.empty(1, 4, 4, dtype=torch.float32).pin_memory())
+                    self._stage_evt = torch.cuda.Event()
+                else:
+                    self._stage_evt.synchronize()       # previous async copy must have left the staging buffer
+                self._stage[0].copy_(torch.from_numpy(np.ascontiguousarray(depth_np, dtype=np.float32)))
+                self._stage[1].copy_(torch.from_numpy(np.ascontiguousarray(T_np, dtype=np.float32)))
+                depth = self._stage[0].to(self.device, non_blocking=True)
+                T = self._stage[1].to(self.device, non_blocking=True)
+                self._stage_evt.record()
+                im = None
+            else:
+                depth = torch.from_numpy(np.ascontiguousarray(depth_np)).float().to(self.device)
+                T = torch.from_numpy(np.ascontiguousarray(T_np)).float().to(self.device)
+                im = torch.from_numpy(np.ascontiguousarray(im_np)).to(self.device).float() / 255.
             data = FrameData(frame_id=np.array([idx]), im_batch=im, im_batch_np=im_np, depth_batch=depth,
                              depth_batch_np=depth_np, T_WC_batch=T, T_WC_batch_np=T_np)
             if self.do_normal:
-                pc = transform.pointcloud_from_depth_torch(depth[0], self.fx, self.fy, self.cx, self.cy)
-                data.normal_batch = transform.estimate_pointcloud_normals(pc)[None, :]
+                if fast:
+                    data.normal_batch = self.sdf_map.engine().ingest_normals(depth[0], self.cam)[None, :]
+                else:
+                    pc = transform.pointcloud_from_depth_torch(depth[0], self.fx, self.fy, self.cx, self.cy)
+                    data.normal_batch = transform.estimate_pointcloud_normals(pc)[None, :]
             out.add_frame_data(data, replace=False)
         return out
 

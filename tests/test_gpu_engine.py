@@ -255,3 +255,22 @@ def test_errors_are_loud():
         eng.pack_weights(torch.zeros(10, device=DEV))
     with pytest.raises(RuntimeError):
         P.make_engine(torch.device("cpu"), O.default_cfg())
+
+
+# ---------------------------------------------------------------------------------- N3
+def test_ingest_normals_matches_torch_restatement():
+    from isdf_b200.engine import make_camera
+    from isdf_b200.geometry import transform
+    H, W = 120, 160
+    depth = C.synthetic_depth(3, H, W, invalid_frac=0.05).to(DEV)
+    depth = 2.0 + 0.5 * torch.sin(torch.arange(W, device=DEV)[None, :] / 20.0) + 0.3 * torch.cos(torch.arange(H, device=DEV)[:, None] / 15.0)
+    depth[5:9, 7:30] = 0.0
+    cam = make_camera(100.0, 100.0, 79.5, 59.5, H, W)
+    eng = _engine(O.default_cfg(), "fp32", max_points=1024)
+    n = eng.ingest_normals(depth, cam)
+    ref = transform.estimate_pointcloud_normals(transform.pointcloud_from_depth_torch(depth, 100.0, 100.0, 79.5, 59.5))
+    nan_a, nan_b = torch.isnan(n[..., 0]), torch.isnan(ref[..., 0])
+    assert torch.equal(nan_a, nan_b)
+    ok = ~nan_a
+    close = (n[ok] - ref[ok]).abs().max(dim=-1).values < 1e-4
+    assert float(close.float().mean()) > 0.999       # near-ties of the neighbour-pair cost may pick another valid pair
