@@ -138,6 +138,7 @@ int tc_create(isdfb_ctx* ctx) {
   d.g_packed = ctx->g_packed;
   d.wout_off = lay.wout_off;
   d.scale_output = ctx->cfg.scale_output;
+  d.skip_ylo = getenv("ISDFB_DW_SKIP_YLO") ? 1 : 0;
   return ISDFB_OK;
 }
 

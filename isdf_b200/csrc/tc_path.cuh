@@ -20,6 +20,7 @@ struct TcDwJob {
 struct TcDwArgs {
   TcDwJob jobs[TC_MAX_JOBS];
   int32_t n_jobs, n_tiles, tile0;
+  int32_t skip_ylo;        // experiment: drop the X_hi*Y_lo pass (Y = layer inputs rounded to bf16)
   const uint8_t *dwl_hi, *dwl_lo;
   size_t dwl_stride;
   float* g_packed;
