@@ -70,7 +70,8 @@ def make_config(wl, precision, rng_mode):
                  "orien_loss": 0},
         "pose_refine": {"pose_lr": 0.0004},
         "b200": {"precision": precision, "rng_mode": rng_mode,
-                 "max_points": 65536 if wl["n_rays"] > 1000 else 32768},
+                 # chunk = a whole number of 148-SM waves of 128-point tiles (no partial last wave)
+                 "max_points": 148 * 128 * 4 if wl["n_rays"] > 1000 else 32768},
     }
 
 
@@ -261,8 +262,8 @@ def main():
             tr.last_is_keyframe = False            # replaces the live (non-key) frame, like add_frame
             tr.add_data(fd)
             h2d += fd.depth_batch_np.nbytes + fd.T_WC_batch_np.nbytes      # fast mode keeps the RGB image on the host
-        losses, _ = tr.step(sync=False)
-        _ = float(losses["total_loss"])            # D2H read of the step's loss
+        losses, _ = tr.step()                      # the reference's call: synchronises and times the step (metrics.py)
+        _ = float(losses["total_loss"])            # the step's loss, delivered D2H (pinned) by the step itself
     e1.record()
     torch.cuda.synchronize(dev)
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -280,13 +281,15 @@ def main():
         eng.profile(True)
         for _ in range(20):
             tr.step(sync=False)
-        pr = eng.profile_read()
+        pr = eng.profile_read()                # 20 steps
         eng.profile(False)
         tr.use_graph = True
         lay_E = 3 + 2 * 21 * 6
         n_units = 4 * (2 * wl["block"] + 2) + 2                     # UMMA products of the chain kernel
-        tiles = (pts_per_step + 127) // 128
-        chain_flops = 2.0 * 256 * 256 * n_units * pts_per_step       # algorithmic (real points, no padding / split passes)
+        n_prof_steps = 20
+        pts_per_launch = pts_per_step * n_prof_steps / max(pr["n_chain"], 1)    # a step is cut into max_points chunks
+        tiles = int((pts_per_launch + 127) // 128)
+        chain_flops = 2.0 * 256 * 256 * n_units * pts_per_launch     # algorithmic (real points, no padding / split passes)
         chain_ms = pr["chain_ms"] / max(pr["n_chain"], 1)
         dw_ms = pr["dw_ms"] / max(pr["n_dw"], 1)
         ach = chain_flops / (chain_ms * 1e-3) / 1e12
@@ -330,8 +333,8 @@ def main():
                                 % (wl["keyframes"] * wl["H"] * wl["W"] * 16 / 1e6, pts_per_step * 0.041)},
                "clocks": clocks,
                "e2e": {"value": e2e_val, "unit": "ray-samples/s", "ms_per_step": e2e_ms / args.steps,
-                       "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": 4,
-                       "api": "isdf.modules.trainer.Trainer.get_data/add_data/step + float(losses['total_loss'])"},
+                       "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": 16,
+                       "api": "isdf.modules.trainer.Trainer.get_data/add_data/step() + float(losses['total_loss'])"},
                "gpu_launches": launches,
                "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(out))

@@ -64,6 +64,10 @@ typedef struct {
   float noise_std;           /* SDFMap.forward noise_std (0 = none)              */
   float inv_count;           /* 1 / (number of valid samples the mean runs over) */
   const float* inv_count_dev;/* optional DEVICE scalar overriding inv_count (no host sync on the count) */
+  /* bounds_method (trainer.py:303-304): both NULL = 'ray' (bound and target direction computed from the
+   * ray inside the kernel, loss.py:13-22,48-53); set to the outputs of isdfb_bounds_pc for 'pc'. */
+  const float* bounds_dev;   /* [R,S]   precomputed bounds                                            */
+  const float* grad_vec_dev; /* [R,S,3] precomputed target directions (row j = 0 of every ray unused)  */
 } isdfb_loss_cfg;
 
 /* Camera intrinsics: transform.py:13-33 (ray_dirs_C, depth_type 'z'). */
@@ -98,7 +102,9 @@ int isdfb_pack_weights(isdfb_ctx* ctx, const float* params_flat, void* stream);
  *   `lin` is torch.linspace(0,1,n_strat+1) (passed in so bin edges are bit-identical).
  *   ib == NULL: T_WC is already per ray ([R,4,4]).  dirs_C_in != NULL: use these camera-frame
  *   directions instead of recomputing them from (ih, iw).  far != NULL: per-ray far limit
- *   (the reference's max_depth tensor) instead of depth + dist_behind.                         */
+ *   (the reference's max_depth tensor) instead of depth + dist_behind.  near != NULL: per-ray near
+ *   limit instead of the scalar min_depth (render passes, trainer.py:1121-1128).  depth_sample may be
+ *   NULL when n_surf == 0 and far is given (gt_depth=None in sample.py:131-178).                   */
 int isdfb_gather_rays(isdfb_ctx* ctx, const float* depth, const float* normals,
                       const int64_t* frame_map, int32_t normals_use_frame_map,
                       const int64_t* ib, const int64_t* ih, const int64_t* iw, int64_t n_rays,
@@ -107,7 +113,7 @@ int isdfb_gather_rays(isdfb_ctx* ctx, const float* depth, const float* normals,
 int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC /*[F,4,4]*/, const int64_t* frame_map,
                       const int64_t* ib, const int64_t* ih, const int64_t* iw,
                       const float* dirs_C_in, const float* depth_sample, const float* far,
-                      const float* u_strat, const float* n_near,
+                      const float* near, const float* u_strat, const float* n_near,
                       const float* lin, int64_t n_rays, int32_t n_strat, int32_t n_surf,
                       const isdfb_camera* cam, float min_depth, float dist_behind,
                       float* pc /*[R,S,3]*/, float* z_vals /*[R,S]*/, float* dirs_C /*[R,3]*/,
@@ -133,6 +139,18 @@ int isdfb_mlp_forward(isdfb_ctx* ctx, const float* x, const float* noise, float 
                       int64_t n, float* sdf, void* stream);
 int isdfb_mlp_forward_grad(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std,
                            int64_t n, float* sdf, float* grad, void* stream);
+
+/* ---- N2: batch-distance bound ("pc", row "next" of SURVEY.md 8f) -------------------------------
+ * loss.bounds_pc (loss.py:56-89): for every sample, the distance to the closest SURFACE sample of the
+ * batch (pc[r,0,:] of every valid ray), negated where z > depth, and the unit vector from that surface
+ * point to the sample (flipped behind the surface; NaN when the two coincide, as in the reference --
+ * K4 substitutes the ray's normal, trainer.py:823-824).  All-pairs R*S x R search tiled through shared
+ * memory.  bounds[R,S]; grad_vec[R,S,3] (row j = 0 is written as the j = 0 direction too but K4 ignores
+ * it: sample 0 targets the surface normal).  ray_valid may be NULL; invalid rays neither receive a bound
+ * nor offer a surface point.                                                                         */
+int isdfb_bounds_pc(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample,
+                    const uint8_t* ray_valid, int64_t n_rays, int32_t n_samples, float* bounds,
+                    float* grad_vec, void* stream);
 
 /* ---- K4: fused training forward/backward ----------------------------------------------
  * Replaces Trainer.sdf_eval_and_loss + total_loss.backward() (trainer.py:768-868, 981):

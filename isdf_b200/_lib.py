@@ -24,7 +24,7 @@ class LossCfg(C.Structure):
     _fields_ = [("trunc_weight", C.c_float), ("trunc_distance", C.c_float), ("eik_weight", C.c_float),
                 ("eik_apply_dist", C.c_float), ("grad_weight", C.c_float), ("orien_loss", C.c_int32),
                 ("loss_type", C.c_int32), ("noise_std", C.c_float), ("inv_count", C.c_float),
-                ("inv_count_dev", C.c_void_p)]
+                ("inv_count_dev", C.c_void_p), ("bounds_dev", C.c_void_p), ("grad_vec_dev", C.c_void_p)]
 
 
 class Camera(C.Structure):
@@ -47,12 +47,13 @@ SIGNATURES = {
     "isdfb_launch_count": (I64, [P]),
     "isdfb_pack_weights": (C.c_int, [P, P, P]),
     "isdfb_gather_rays": (C.c_int, [P, P, P, P, I32, P, P, P, I64, C.POINTER(Camera), P, P, P, P]),
-    "isdfb_sample_rays": (C.c_int, [P, P, P, P, P, P, P, P, P, P, P, P, I64, I32, I32, C.POINTER(Camera), F, F,
+    "isdfb_sample_rays": (C.c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I32, I32, C.POINTER(Camera), F, F,
                                     P, P, P, P, P]),
     "isdfb_ingest_normals": (C.c_int, [P, P, C.POINTER(Camera), P, P]),
     "isdfb_pe_encode": (C.c_int, [P, P, I64, P, P]),
     "isdfb_mlp_forward": (C.c_int, [P, P, P, F, I64, P, P]),
     "isdfb_mlp_forward_grad": (C.c_int, [P, P, P, F, I64, P, P, P]),
+    "isdfb_bounds_pc": (C.c_int, [P, P, P, P, P, I64, I32, P, P, P]),
     "isdfb_train_fwd_bwd": (C.c_int, [P, P, P, P, P, P, P, P, P, I64, I32, C.POINTER(LossCfg), P, P, P, P, P]),
     "isdfb_zero_grad": (C.c_int, [P, P]),
     "isdfb_export_grads": (C.c_int, [P, P, P]),

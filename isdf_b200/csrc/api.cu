@@ -7,11 +7,13 @@ char g_isdfb_create_err[512] = "";
 int sample_gather(isdfb_ctx*, const float*, const float*, const int64_t*, int, const int64_t*, const int64_t*,
                   const int64_t*, int64_t, const isdfb_camera*, float*, float*, uint8_t*, cudaStream_t);
 int sample_along(isdfb_ctx*, const float*, const int64_t*, const int64_t*, const int64_t*, const int64_t*,
-                 const float*, const float*, const float*, const float*, const float*, const float*, int64_t, int, int,
-                 const isdfb_camera*, float, float, float*, float*, float*, float*, cudaStream_t);
+                 const float*, const float*, const float*, const float*, const float*, const float*, const float*, int64_t,
+                 int, int, const isdfb_camera*, float, float, float*, float*, float*, float*, cudaStream_t);
 int sample_frame_bins(isdfb_ctx*, float*, const float*, const uint8_t*, const int64_t*, const int64_t*,
                       const int64_t*, int64_t, int, int, int, int, int, float*, float*, cudaStream_t);
 int sample_ingest_normals(isdfb_ctx*, const float*, const isdfb_camera*, float*, cudaStream_t);
+int bounds_pc_launch(isdfb_ctx*, const float*, const float*, const float*, const uint8_t*, int64_t, int32_t, float*,
+                     float*, cudaStream_t);
 int tc_create(isdfb_ctx* ctx);
 void tc_destroy(isdfb_ctx* ctx);
 int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n,
@@ -152,16 +154,18 @@ int isdfb_gather_rays(isdfb_ctx* ctx, const float* depth, const float* normals, 
 
 int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC, const int64_t* frame_map, const int64_t* ib,
                       const int64_t* ih, const int64_t* iw, const float* dirs_C_in, const float* depth_sample,
-                      const float* far, const float* u_strat, const float* n_near, const float* lin, int64_t n_rays, int32_t n_strat, int32_t n_surf,
+                      const float* far, const float* near, const float* u_strat, const float* n_near, const float* lin, int64_t n_rays, int32_t n_strat, int32_t n_surf,
                       const isdfb_camera* cam, float min_depth, float dist_behind, float* pc, float* z_vals,
                       float* dirs_C, float* T_WC_sample, void* stream) {
   ENTER(ctx);
   if (n_rays == 0) return ISDFB_OK;
-  if (!T_WC || (!dirs_C_in && (!ih || !iw)) || !depth_sample || !u_strat || !lin || !cam || !pc || !z_vals || !dirs_C || !T_WC_sample)
+  if (!depth_sample && (n_surf > 0 || !far))
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_rays: depth_sample may be NULL only with n_surf == 0 and a far limit");
+  if (!T_WC || (!dirs_C_in && (!ih || !iw)) || !u_strat || !lin || !cam || !pc || !z_vals || !dirs_C || !T_WC_sample)
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_rays: null argument");
   if (n_strat < 1 || n_surf < 0 || (n_surf > 1 && !n_near))
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_rays: bad sample counts (n_strat %d n_surf %d)", n_strat, n_surf);
-  return sample_along(ctx, T_WC, frame_map, ib, ih, iw, dirs_C_in, depth_sample, far, u_strat, n_near, lin, n_rays, n_strat,
+  return sample_along(ctx, T_WC, frame_map, ib, ih, iw, dirs_C_in, depth_sample, far, near, u_strat, n_near, lin, n_rays, n_strat,
                       n_surf, cam, min_depth, dist_behind, pc, z_vals, dirs_C, T_WC_sample, st);
 }
 
@@ -198,6 +202,16 @@ int isdfb_mlp_forward_grad(isdfb_ctx* ctx, const float* x, const float* noise, f
   return tc_forward(ctx, x, noise, noise_std, n, sdf, grad, st);
 }
 
+int isdfb_bounds_pc(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample,
+                    const uint8_t* ray_valid, int64_t n_rays, int32_t n_samples, float* bounds, float* grad_vec,
+                    void* stream) {
+  ENTER(ctx);
+  if (n_rays == 0) return ISDFB_OK;
+  if (!pc || !z_vals || !depth_sample || !bounds || !grad_vec) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_bounds_pc: null argument");
+  if (n_samples < 1) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "n_samples %d", n_samples);
+  return bounds_pc_launch(ctx, pc, z_vals, depth_sample, ray_valid, n_rays, n_samples, bounds, grad_vec, st);
+}
+
 int isdfb_train_fwd_bwd(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample,
                         const float* dirs_C, const float* T_WC_sample, const float* norm_sample,
                         const float* noise, const uint8_t* ray_valid, int64_t n_rays, int32_t n_samples,
@@ -213,6 +227,8 @@ int isdfb_train_fwd_bwd(isdfb_ctx* ctx, const float* pc, const float* z_vals, co
   if (loss->loss_type != 1 && loss->loss_type != 2)
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "Must be L1 or L2");   // loss.py:143
   if (n_samples < 1) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "n_samples %d", n_samples);
+  if ((loss->bounds_dev == nullptr) != (loss->grad_vec_dev == nullptr))
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_train_fwd_bwd: bounds_dev and grad_vec_dev must be given together ('pc') or not at all ('ray')");
   if (ctx->cfg.precision == ISDFB_PREC_FP32)
     return simt_train(ctx, pc, z_vals, depth_sample, dirs_C, T_WC_sample, norm_sample, noise, ray_valid, n_rays,
                       n_samples, loss, sdf, grad, loss_mat, loss_sums, st);

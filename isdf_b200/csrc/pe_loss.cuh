@@ -113,6 +113,35 @@ __device__ __forceinline__ LossPoint loss_point(const isdfb_loss_cfg& c, float s
   return o;
 }
 
+// Bound and normal-term target of sample (r, j), global sample index pg = r*S + j.
+//   'ray'  (c.bounds_dev == NULL): bnd = ||d_C|| (depth - z), u = -R_WC d_C      (loss.py:13-22, 48-53)
+//   'pc'   (c.bounds_dev != NULL): bnd / u precomputed by isdfb_bounds_pc        (loss.py:56-89); a NaN
+//          direction (sample on top of its closest surface point) becomes the ray's normal (trainer.py:823-824)
+// Sample 0 always targets the surface normal when normals are given (trainer.py:819-820).
+__device__ __forceinline__ void loss_bound_target(const isdfb_loss_cfg& c, int64_t pg, int64_t r, int j,
+                                                  const float* __restrict__ dirs_C, const float* __restrict__ depth,
+                                                  const float* __restrict__ z_vals, const float* __restrict__ T_WC,
+                                                  const float* __restrict__ normals, float& bnd, float u[3]) {
+  const float dc[3] = {dirs_C[r * 3], dirs_C[r * 3 + 1], dirs_C[r * 3 + 2]};
+  if (c.bounds_dev) {
+    bnd = c.bounds_dev[pg];
+  } else {
+    const float nrm = sqrtf(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]);
+    bnd = nrm * (depth[r] - z_vals[pg]);
+  }
+  if (j == 0 && normals) {
+    u[0] = normals[r * 3]; u[1] = normals[r * 3 + 1]; u[2] = normals[r * 3 + 2];
+  } else if (c.grad_vec_dev) {
+    u[0] = c.grad_vec_dev[pg * 3]; u[1] = c.grad_vec_dev[pg * 3 + 1]; u[2] = c.grad_vec_dev[pg * 3 + 2];
+    if (u[0] != u[0] && normals) { u[0] = normals[r * 3]; u[1] = normals[r * 3 + 1]; u[2] = normals[r * 3 + 2]; }
+  } else {
+    const float* Tm = T_WC + r * 16;
+    u[0] = -(Tm[0] * dc[0] + Tm[1] * dc[1] + Tm[2] * dc[2]);
+    u[1] = -(Tm[4] * dc[0] + Tm[5] * dc[1] + Tm[6] * dc[2]);
+    u[2] = -(Tm[8] * dc[0] + Tm[9] * dc[1] + Tm[10] * dc[2]);
+  }
+}
+
 // softplus(beta=100, threshold=20) and its first/second derivative factors (fc_map.py:54)
 __device__ __forceinline__ void softplus100(float z, float& h, float& sig) {
   float bz = 100.f * z;

@@ -33,6 +33,7 @@ __global__ void sample_rays_kernel(const float* __restrict__ T_WC, const int64_t
                                    const int64_t* __restrict__ ib, const int64_t* __restrict__ ih,
                                    const int64_t* __restrict__ iw, const float* __restrict__ dirs_in,
                                    const float* __restrict__ depth_s, const float* __restrict__ far_in,
+                                   const float* __restrict__ near_in,
                                    const float* __restrict__ u_strat, const float* __restrict__ n_near,
                                    const float* __restrict__ lin, int64_t n_rays, int n_strat, int n_surf,
                                    isdfb_camera cam, float min_depth, float dist_behind,
@@ -58,8 +59,9 @@ __global__ void sample_rays_kernel(const float* __restrict__ T_WC, const int64_t
   float wx = __fadd_rn(__fadd_rn(__fmul_rn(T[0], dx), __fmul_rn(T[1], dy)), __fmul_rn(T[2], dz));
   float wy = __fadd_rn(__fadd_rn(__fmul_rn(T[4], dx), __fmul_rn(T[5], dy)), __fmul_rn(T[6], dz));
   float wz = __fadd_rn(__fadd_rn(__fmul_rn(T[8], dx), __fmul_rn(T[9], dy)), __fmul_rn(T[10], dz));
-  float d = depth_s[r];
+  float d = depth_s ? depth_s[r] : 0.f;
   float far = far_in ? far_in[r] : __fadd_rn(d, dist_behind);
+  if (near_in) min_depth = near_in[r];                   // per-ray near limit (render passes, trainer.py:1121-1128)
   float z;
   if (j < n_surf) {
     if (j == 0) {
@@ -224,14 +226,14 @@ int sample_gather(isdfb_ctx* ctx, const float* depth, const float* normals, cons
 
 int sample_along(isdfb_ctx* ctx, const float* T_WC, const int64_t* frame_map, const int64_t* ib,
                  const int64_t* ih, const int64_t* iw, const float* dirs_in, const float* depth_sample,
-                 const float* far_in, const float* u_strat,
+                 const float* far_in, const float* near_in, const float* u_strat,
                  const float* n_near, const float* lin, int64_t n_rays, int n_strat, int n_surf,
                  const isdfb_camera* cam, float min_depth, float dist_behind, float* pc, float* z_vals,
                  float* dirs_C, float* T_out, cudaStream_t st) {
   if (n_rays == 0) return ISDFB_OK;
   int64_t total = n_rays * (n_strat + n_surf);
   sample_rays_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      T_WC, frame_map, ib, ih, iw, dirs_in, depth_sample, far_in, u_strat, n_near, lin, n_rays, n_strat, n_surf, *cam,
+      T_WC, frame_map, ib, ih, iw, dirs_in, depth_sample, far_in, near_in, u_strat, n_near, lin, n_rays, n_strat, n_surf, *cam,
       min_depth, dist_behind, pc, z_vals, dirs_C, T_out);
   ISDFB_LAUNCHED(ctx);
   ISDFB_CUDA_OK(ctx, cudaGetLastError());

@@ -236,18 +236,8 @@ __global__ void loss_kernel(isdfb_loss_cfg lc, const float* __restrict__ sdf, co
     bool valid = ray_valid ? (ray_valid[r] != 0) : true;
     float sb = 0.f, gb[3] = {0.f, 0.f, 0.f}, tot = 0.f;
     if (valid) {
-      float dc[3] = {dirs_C[r * 3], dirs_C[r * 3 + 1], dirs_C[r * 3 + 2]};
-      float nrm = sqrtf(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]);
-      float bnd = nrm * (depth[r] - z_vals[p]);
-      float u[3];
-      if (j == 0 && normals) {
-        u[0] = normals[r * 3]; u[1] = normals[r * 3 + 1]; u[2] = normals[r * 3 + 2];
-      } else {
-        const float* T = T_WC + r * 16;     // -dir_W = -(R_WC d_C)   (loss.py:48-53)
-        u[0] = -(T[0] * dc[0] + T[1] * dc[1] + T[2] * dc[2]);
-        u[1] = -(T[4] * dc[0] + T[5] * dc[1] + T[6] * dc[2]);
-        u[2] = -(T[8] * dc[0] + T[9] * dc[1] + T[10] * dc[2]);
-      }
+      float bnd, u[3];
+      loss_bound_target(lc, p, r, j, dirs_C, depth, z_vals, T_WC, normals, bnd, u);
       float gg[3] = {g[i * 3], g[i * 3 + 1], g[i * 3 + 2]};
       isdfb_loss_cfg c = lc;
       if (j == 0 && !normals) c.grad_weight = lc.grad_weight;   // (normals always given when grad_weight != 0)

@@ -504,18 +504,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
                 const int jx = (int)(pg - r * args.S);
                 const bool valid = args.ray_valid ? (args.ray_valid[r] != 0) : true;
                 if (valid) {
-                  const float dc[3] = {args.dirs_C[r * 3], args.dirs_C[r * 3 + 1], args.dirs_C[r * 3 + 2]};
-                  const float nrm = sqrtf(dc[0] * dc[0] + dc[1] * dc[1] + dc[2] * dc[2]);
-                  const float bnd = nrm * (args.depth[r] - args.z_vals[pg]);
-                  float uu[3];
-                  if (jx == 0 && args.normals) {
-                    uu[0] = args.normals[r * 3]; uu[1] = args.normals[r * 3 + 1]; uu[2] = args.normals[r * 3 + 2];
-                  } else {
-                    const float* Tm = args.T_WC + r * 16;
-                    uu[0] = -(Tm[0] * dc[0] + Tm[1] * dc[1] + Tm[2] * dc[2]);
-                    uu[1] = -(Tm[4] * dc[0] + Tm[5] * dc[1] + Tm[6] * dc[2]);
-                    uu[2] = -(Tm[8] * dc[0] + Tm[9] * dc[1] + Tm[10] * dc[2]);
-                  }
+                  float bnd, uu[3];
+                  loss_bound_target(args.loss, pg, r, jx, args.dirs_C, args.depth, args.z_vals, args.T_WC, args.normals, bnd, uu);
                   const LossPoint o = loss_point(args.loss, sdf_reg, g, bnd, uu);
                   sb = o.sbar; gb[0] = o.gbar[0]; gb[1] = o.gbar[1]; gb[2] = o.gbar[2];
                   tot = o.total;

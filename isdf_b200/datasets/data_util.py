@@ -12,8 +12,10 @@ _FIELDS = ("frame_id", "im_batch", "im_batch_np", "depth_batch", "depth_batch_np
 class _Growable:
     """Rows appended into a capacity-doubling buffer; `view` is the live [n, ...] prefix."""
 
-    def __init__(self):
+    def __init__(self, wrap=None):
         self.buf, self.n = None, 0
+        if wrap is not None:                 # adopt the caller's rows as-is (no copy, no spare capacity)
+            self.buf, self.n = wrap, wrap.shape[0]
 
     def append(self, rows):
         k = rows.shape[0]
@@ -59,10 +61,8 @@ class FrameData:
 
     def __setattr__(self, name, value):
         if name in _FIELDS:
-            g = _Growable()
             if value is not None:
-                g.append(value)
-                self._store[name] = g
+                self._store[name] = _Growable(wrap=value)
             else:
                 self._store.pop(name, None)
         else:
@@ -72,9 +72,8 @@ class FrameData:
         if rows is None:
             return
         g = self._store.get(name)
-        if g is None:
-            g = self._store[name] = _Growable()
-            g.append(rows)
+        if g is None:       # first rows are adopted, not copied (the reference assigns them too, data_util.py:52-60)
+            self._store[name] = _Growable(wrap=rows)
         elif replace:
             g.replace_last(rows)
         else:

@@ -109,18 +109,19 @@ class Engine:
         return d_out, n_out, valid
 
     def sample_rays(self, T_WC, ib, ih, iw, depth_sample, u_strat, n_near, lin, n_strat, n_surf, cam,
-                    min_depth, dist_behind, frame_map=None, dirs_C_in=None, far=None):
+                    min_depth, dist_behind, frame_map=None, dirs_C_in=None, far=None, near=None):
         dev = self.device
         T_WC = _f32(T_WC, "T_WC", dev)
         ib, ih, iw = _i64(ib, "indices_b", dev), _i64(ih, "indices_h", dev), _i64(iw, "indices_w", dev)
         dirs_C_in = _f32(dirs_C_in, "dirs_C", dev)
         far = _f32(far, "max_depth", dev)
+        near = _f32(near, "min_depth", dev)
         frame_map = _i64(frame_map, "frame_map", dev)
         depth_sample = _f32(depth_sample, "depth_sample", dev)
         u_strat = _f32(u_strat, "u_strat", dev)
         n_near = _f32(n_near, "n_near", dev)
         lin = _f32(lin, "lin", dev)
-        R = depth_sample.numel()
+        R = depth_sample.numel() if depth_sample is not None else far.numel()
         S = n_strat + n_surf
         if u_strat.shape != (R, n_strat):
             raise ValueError("u_strat must be [%d,%d]" % (R, n_strat))
@@ -131,7 +132,7 @@ class Engine:
         dirs_C = torch.empty(R, 3, dtype=torch.float32, device=dev)
         T_s = torch.empty(R, 4, 4, dtype=torch.float32, device=dev)
         self._ck(self.lib.isdfb_sample_rays(self._ctx, _ptr(T_WC), _ptr(frame_map), _ptr(ib), _ptr(ih), _ptr(iw),
-                                            _ptr(dirs_C_in), _ptr(depth_sample), _ptr(far), _ptr(u_strat), _ptr(n_near), _ptr(lin), R,
+                                            _ptr(dirs_C_in), _ptr(depth_sample), _ptr(far), _ptr(near), _ptr(u_strat), _ptr(n_near), _ptr(lin), R,
                                             int(n_strat), int(n_surf), C.byref(cam), float(min_depth),
                                             float(dist_behind), _ptr(pc), _ptr(z), _ptr(dirs_C), _ptr(T_s),
                                             self._stream()))
@@ -170,6 +171,21 @@ class Engine:
         self._ck(self.lib.isdfb_mlp_forward(self._ctx, _ptr(x), _ptr(noise), float(noise_std), n, _ptr(sdf),
                                             self._stream()))
         return sdf
+
+    # ---- N2 ----------------------------------------------------------
+    def bounds_pc(self, pc, z_vals, depth_sample, ray_valid=None):
+        """loss.bounds_pc (loss.py:56-89): bounds [R,S] and target directions [R,S,3] (row 0 unused)."""
+        dev = self.device
+        pc, z_vals = _f32(pc, "pc", dev), _f32(z_vals, "z_vals", dev)
+        depth_sample = _f32(depth_sample, "depth_sample", dev)
+        R, S = z_vals.shape
+        if ray_valid is not None:
+            ray_valid = ray_valid.to(torch.uint8).contiguous()
+        bounds = torch.empty(R, S, dtype=torch.float32, device=dev)
+        vec = torch.empty(R, S, 3, dtype=torch.float32, device=dev)
+        self._ck(self.lib.isdfb_bounds_pc(self._ctx, _ptr(pc), _ptr(z_vals), _ptr(depth_sample), _ptr(ray_valid),
+                                          R, S, _ptr(bounds), _ptr(vec), self._stream()))
+        return bounds, vec
 
     # ---- K4 ----------------------------------------------------------
     def train_fwd_bwd(self, pc, z_vals, depth_sample, dirs_C, T_WC_sample, norm_sample, noise, loss_cfg,
@@ -265,7 +281,7 @@ class _DevView:
 
 
 def make_loss_cfg(trunc_weight, trunc_distance, eik_weight, eik_apply_dist, grad_weight, orien_loss, loss_type,
-                  noise_std, inv_count, inv_count_dev=None):
+                  noise_std, inv_count, inv_count_dev=None, bounds=None, grad_vec=None):
     lc = _lib.LossCfg()
     lc.trunc_weight, lc.trunc_distance = float(trunc_weight), float(trunc_distance)
     lc.eik_weight, lc.eik_apply_dist = float(eik_weight), float(eik_apply_dist)
@@ -282,6 +298,15 @@ def make_loss_cfg(trunc_weight, trunc_distance, eik_weight, eik_apply_dist, grad
             raise TypeError("inv_count_dev must be a float32 CUDA scalar")
         lc.inv_count_dev = inv_count_dev.data_ptr()
         lc._keepalive = inv_count_dev
+    lc.bounds_dev = lc.grad_vec_dev = None
+    if (bounds is None) != (grad_vec is None):
+        raise ValueError("bounds and grad_vec (the outputs of Engine.bounds_pc) go together")
+    if bounds is not None:
+        for t, nm in ((bounds, "bounds"), (grad_vec, "grad_vec")):
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise TypeError("%s must be a contiguous float32 CUDA tensor" % nm)
+        lc.bounds_dev, lc.grad_vec_dev = bounds.data_ptr(), grad_vec.data_ptr()
+        lc._keepalive_pc = (bounds, grad_vec)
     return lc
 
 

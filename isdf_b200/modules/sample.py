@@ -96,19 +96,29 @@ def sample_along_rays(T_WC, min_depth, max_depth, n_stratified_samples, n_surf_s
         raise NotImplementedError("grad=True (pose refinement) is not part of the hot path")
     dev = T_WC.device
     eng = engine or _engine(dev)
+    dirs_C = dirs_C.reshape(-1, 3)
     R = dirs_C.shape[0]
-    if gt_depth is None or n_surf_samples <= 0:
-        raise NotImplementedError("isdf_b200 samples around a measured depth (gt_depth required)")
-    if not torch.is_tensor(max_depth):
-        raise TypeError("max_depth must be a per-ray tensor (depth + dist_behind_surf)")
     rd = rng_device or dev
-    u = torch.rand(R, n_stratified_samples, device=rd).to(dev)
-    near = torch.normal(torch.zeros(R, n_surf_samples - 1), 0.1).to(dev)
-    S = n_stratified_samples + n_surf_samples
+    with_surf = gt_depth is not None and n_surf_samples > 0
+    n_surf = n_surf_samples if with_surf else 0       # gt_depth=None: stratified samples only (sample.py:158)
+    S = n_stratified_samples + n_surf
     if R == 0:
         return torch.empty(0, S, 3, device=dev), torch.empty(0, S, device=dev)
+
+    def per_ray(v):
+        return v.to(dev).float().reshape(-1).expand(R) if torch.is_tensor(v) else torch.full((R,), float(v), device=dev)
+
+    far = per_ray(max_depth).contiguous()
+    near = per_ray(min_depth).contiguous() if torch.is_tensor(min_depth) else None
+    if not torch.is_tensor(max_depth) and near is None:
+        near = per_ray(min_depth)                     # scalar/scalar: same bins up to the rounding of linspace
+    u = torch.rand(R, n_stratified_samples, device=rd).to(dev)
+    off = torch.normal(torch.zeros(R, n_surf - 1), 0.1).to(dev) if n_surf > 1 else None      # CPU RNG (quirk Q6)
     lin = torch.linspace(0, 1, n_stratified_samples + 1).to(dev)
     cam = make_camera(1.0, 1.0, 0.0, 0.0, 1, 1)           # unused: directions are given explicitly
-    pc, z, _, _ = eng.sample_rays(T_WC, None, None, None, gt_depth, u, near, lin, n_stratified_samples,
-                                  n_surf_samples, cam, float(min_depth), 0.0, dirs_C_in=dirs_C, far=max_depth)
+    T = T_WC.reshape(-1, 4, 4)
+    ib = None if T.shape[0] == R else torch.zeros(R, dtype=torch.int64, device=dev)       # one pose for all rays
+    pc, z, _, _ = eng.sample_rays(T, ib, None, None, gt_depth if with_surf else None, u, off, lin,
+                                  n_stratified_samples, n_surf, cam, 0.0 if near is not None else float(min_depth),
+                                  0.0, dirs_C_in=dirs_C.contiguous(), far=far, near=near)
     return pc, z

@@ -34,7 +34,7 @@ from . import embedding, fc_map, render, sample
 
 _OUT_OF_SCOPE = ("view_sdf", "latest_frame_vis", "update_vis_vars", "frames_vis", "draw_3D", "draw_obj_3D",
                  "obj_slices_vis", "write_slices", "write_mesh", "mesh_rec", "eval_fixed", "eval_sdf",
-                 "eval_object_sdf", "eval_mesh", "compute_slices", "sdf_fn", "grad_fn")
+                 "eval_object_sdf", "eval_mesh", "compute_slices")
 
 
 class FusedAdamW:
@@ -42,7 +42,10 @@ class FusedAdamW:
 
     def __init__(self, sdf_map, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8):
         self.sdf_map = sdf_map
-        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        # same keys torch.optim.AdamW writes into a checkpoint, so the reference's optimiser can load ours
+        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                             foreach=None, capturable=False, differentiable=False, fused=None,
+                             decoupled_weight_decay=True)
         self.param_groups = [dict(self.defaults, params=list(sdf_map.parameters()))]
         self.step_count = 0
         self.exp_avg = None
@@ -129,6 +132,8 @@ class Trainer:
         self.use_graph = bool(b200.get("cuda_graph", 1))
         self._graph = None
         self._graph_seen = None
+        self._plist = None
+        self._loss_host = None
         self._stage = None
         self.dist_world, self.dist_rank = parallel.world()
 
@@ -266,7 +271,13 @@ class Trainer:
         return self._dirs_C
 
     def set_directions(self):
+        """trainer.py:383-411: full-resolution directions are built lazily (`dirs_C`); the two reduced
+        grids feed the forward-only renders (row N1)."""
         self._dirs_C = None
+        self.dirs_C_vis = transform.ray_dirs_C(1, self.H_vis, self.W_vis, self.fx_vis, self.fy_vis, self.cx_vis,
+                                               self.cy_vis, self.device).view(1, -1, 3)
+        self.dirs_C_vis_up = transform.ray_dirs_C(1, self.H_vis_up, self.W_vis_up, self.fx_vis_up, self.fy_vis_up,
+                                                  self.cx_vis_up, self.cy_vis_up, self.device).view(1, -1, 3)
 
     def load_networks(self):
         pe = embedding.PostionalEncoding(min_deg=0, max_deg=self.n_embed_funcs, scale=self.scale_input,
@@ -279,8 +290,22 @@ class Trainer:
         self.optimiser = FusedAdamW(self.sdf_map, lr=self.learning_rate, weight_decay=self.weight_decay)
 
     def load_checkpoint(self, checkpoint_load_file):
+        """Reads the reference's checkpoint files (train.py:207-219: step / model_state_dict /
+        optimizer_state_dict / loss).  Like the reference (trainer.py:441-444) only the model is restored;
+        `load_optimiser_state` restores AdamW's moments too (row N4)."""
         chk = torch.load(checkpoint_load_file, map_location=self.device)
         self.sdf_map.load_state_dict(chk["model_state_dict"])
+        return chk
+
+    def load_optimiser_state(self, checkpoint):
+        chk = checkpoint if isinstance(checkpoint, dict) else torch.load(checkpoint, map_location=self.device)
+        self.optimiser.load_state_dict(chk["optimizer_state_dict"])
+
+    def save_checkpoint(self, filename, step=None, loss=None):
+        """Same dictionary the reference driver writes (train.py:207-219); loadable by the reference."""
+        sd = {k: v.detach().clone() for k, v in self.sdf_map.state_dict().items()}
+        torch.save({"step": step, "model_state_dict": sd, "optimizer_state_dict": self.optimiser.state_dict(),
+                    "loss": None if loss is None else float(loss)}, filename)
 
     # ---- data (trainer.py:447-582) ----------------------------------------------------------
     def load_data(self):
@@ -463,13 +488,17 @@ class Trainer:
         """K4 (+K5).  Returns (total_loss, losses, loss_approx, frame_avg_loss) like the reference;
         the parameter gradient of total_loss is left in the engine's gradient buffer (the fused
         kernel already did the double back-prop), so no .backward() follows."""
-        if self.bounds_method != "ray":
-            raise NotImplementedError("bounds_method %r: only 'ray' is fused ('pc' is a next-row item, 'normal' "
-                                      "raises in the reference itself)" % self.bounds_method)
+        if self.bounds_method == "normal":
+            raise TypeError("bounds_method 'normal' is broken in the reference itself (loss.py:29 calls "
+                            "bounds_ray with 3 of its 5 arguments) and is not supported")
         eng = self.sdf_map.engine()
         pc = sample_pts["pc"]
         R, S = pc.shape[0], pc.shape[1]
         ray_valid = sample_pts.get("ray_valid")
+        pc_bounds = pc_vec = None
+        if self.bounds_method == "pc":          # N2: all-pairs batch-distance bound (loss.py:56-89)
+            pc_bounds, pc_vec = eng.bounds_pc(pc, sample_pts["z_vals"], sample_pts["depth_sample"],
+                                              ray_valid=ray_valid)
         noise = None
         if self.noise_std is not None:
             noise = torch.randn(R, S, device=self.rng_device or self.device).to(self.device)
@@ -482,7 +511,7 @@ class Trainer:
             inv_dev = (1.0 / cnt.clamp_min(1.0)).reshape(1)
         lc = make_loss_cfg(self.trunc_weight, self.trunc_distance, self.eik_weight, self.eik_apply_dist,
                            self.grad_weight, self.orien_loss, self.loss_type, self.noise_std or 0.0, inv_count,
-                           inv_count_dev=inv_dev)
+                           inv_count_dev=inv_dev, bounds=pc_bounds, grad_vec=pc_vec)
         self._loss_sums.zero_()
         eng.zero_grad()
         sdf, _, loss_mat, sums = eng.train_fwd_bwd(pc, sample_pts["z_vals"], sample_pts["depth_sample"],
@@ -497,13 +526,22 @@ class Trainer:
                 losses["grad_loss"] = host[1]
             if self.eik_weight != 0:
                 losses["eikonal_loss"] = host[2]
+            total_loss = means[3]
         else:
-            losses = {"sdf_loss": means[0]}
+            # fast mode: the four means are delivered to pinned host memory by the step itself (an async D2H
+            # copy on the step's stream -- a memcpy node of the captured graph).  They are valid once the step
+            # has completed: Trainer.step() synchronises like the reference's (metrics.py:27-30); with
+            # step(sync=False) the caller synchronises before reading.
+            if self._loss_host is None:
+                self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self._loss_host.copy_(means, non_blocking=True)
+            host = self._loss_host
+            losses = {"sdf_loss": host[0]}
             if self.grad_weight != 0:
-                losses["grad_loss"] = means[1]
+                losses["grad_loss"] = host[1]
             if self.eik_weight != 0:
-                losses["eikonal_loss"] = means[2]
-        total_loss = means[3]
+                losses["eikonal_loss"] = host[2]
+            total_loss = host[3]
         losses["total_loss"] = total_loss
         self.last_sdf, self.last_loss_mat = sdf, loss_mat
         loss_approx = frame_avg_loss = None
@@ -545,10 +583,18 @@ class Trainer:
         return losses
 
     def _graph_key(self):
+        """Everything a captured step bakes in: keyframe buffers (count + addresses), noise level, the flat
+        parameter buffer and the parameters' version counters (an in-place load_state_dict must re-pack).
+        Kept cheap -- it runs on the host before every replay while the GPU is idle."""
         f = self.frames
-        return (len(f), f.depth_batch.data_ptr(), f.T_WC_batch.data_ptr(),
-                f.normal_batch.data_ptr() if f.normal_batch is not None else 0, f.frame_avg_losses.data_ptr(),
-                self.noise_std, self.sdf_map.flat_parameters().data_ptr())
+        m = self.sdf_map
+        if m._flat is None or self._plist is None:
+            m.flat_parameters()
+            self._plist = list(m.parameters())
+        nb = f.normal_batch
+        return (len(f), f.depth_batch.data_ptr(), f.T_WC_batch.data_ptr(), 0 if nb is None else nb.data_ptr(),
+                f.frame_avg_losses.data_ptr(), self.noise_std, m._flat.data_ptr(),
+                tuple([p._version for p in self._plist]))
 
     def _step_graphed(self):
         """fast mode: the step as CUDA-graph launches -- one graph on a single GPU; with data parallelism
@@ -596,5 +642,94 @@ class Trainer:
         self.steps_since_frame += 1
         return losses, step_time
 
-    def get_sdf_grid_pc(self, *a, **k):
-        raise NotImplementedError("grid / mesh extraction is outside the hot path")
+    # ---- forward-only inference (row N1 of SURVEY.md 8f) --------------------------------------
+    def set_scene_properties(self, scene_mesh=None, T_extent_to_scene=None, bounds_extents=None, scene_center=None):
+        """Scene box -> PE transform, grid scale and the grid_dim^3 query points (trainer.py:103-156).
+        The reference derives the oriented box with trimesh (absent here): pass it explicitly
+        (`T_extent_to_scene` world->box 4x4 and `bounds_extents` [3], i.e. the two return values of
+        trimesh.bounds.oriented_bounds), or an [N,3] point array / an object with `.vertices`, for
+        which the AXIS-ALIGNED box is used."""
+        if "realsense_franka" in self.dataset_format and T_extent_to_scene is None:
+            ws = self.config["workspace"]
+            a = np.deg2rad(ws["rotate_z"])
+            T_extent_to_scene = np.eye(4)
+            T_extent_to_scene[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+            T_extent_to_scene[:3, 3] = np.array(ws["offset"])
+            bounds_extents, scene_center = np.array(ws["extents"]), np.array(ws["center"])
+        if T_extent_to_scene is None:
+            if scene_mesh is None:
+                raise ValueError("set_scene_properties needs an oriented box or a point set")
+            pts = np.asarray(getattr(scene_mesh, "vertices", scene_mesh), dtype=np.float64).reshape(-1, 3)
+            lo, hi = pts.min(axis=0), pts.max(axis=0)
+            T_extent_to_scene = np.eye(4)
+            T_extent_to_scene[:3, 3] = -(lo + hi) / 2
+            bounds_extents = hi - lo
+            scene_center = (lo + hi) / 2
+        T_extent_to_scene = np.asarray(T_extent_to_scene, dtype=np.float64)
+        bounds_extents = np.asarray(bounds_extents, dtype=np.float64)
+        self.scene_center = scene_center
+        self.inv_bounds_transform = torch.from_numpy(T_extent_to_scene).float().to(self.device)
+        self.bounds_transform_np = np.linalg.inv(T_extent_to_scene)
+        self.bounds_transform = torch.from_numpy(self.bounds_transform_np).float().to(self.device)
+        grid_range = [-1.0, 1.0]
+        self.scene_scale_np = bounds_extents / ((grid_range[1] - grid_range[0]) * 0.9)
+        self.scene_scale = torch.from_numpy(self.scene_scale_np).float().to(self.device)
+        self.inv_scene_scale = 1. / self.scene_scale
+        self.grid_pc = transform.make_3D_grid(grid_range, self.grid_dim, self.device, transform=self.bounds_transform,
+                                              scale=self.scene_scale).view(-1, 3).contiguous()
+        self.up_ix = int(np.argmax(np.abs(np.matmul(self.up, self.bounds_transform_np[:3, :3]))))
+        self.grid_up = self.bounds_transform_np[:3, self.up_ix]
+        self.up_aligned = np.dot(self.grid_up, self.up) > 0
+        self.crop_dist = 0.1 if "franka" in self.dataset_format else 0.25
+
+    def get_sdf_grid(self):
+        """SDF on the grid_dim^3 lattice (trainer.py:1426-1444): one K2 call, chunked inside the library
+        (the reference loops fc_map.chunks over 100 000-point slices)."""
+        if getattr(self, "grid_pc", None) is None:
+            raise RuntimeError("call set_scene_properties first (grid_pc is not set)")
+        with torch.no_grad():
+            sdf = self.sdf_map(self.grid_pc)
+        return sdf.view(self.grid_dim, self.grid_dim, self.grid_dim)
+
+    def get_sdf_grid_pc(self, include_gt=False, mask_near_pc=False):
+        """[dim,dim,dim,4] numpy array of (x, y, z, sdf) (trainer.py:1446-1481)."""
+        if include_gt or mask_near_pc:
+            raise NotImplementedError("GT-SDF interpolation and the KD-tree crop belong to the evaluation / "
+                                      "visualisation tool-chain (out of scope)")
+        sdf_grid = self.get_sdf_grid()
+        grid_pc = self.grid_pc.reshape(self.grid_dim, self.grid_dim, self.grid_dim, 3)
+        return torch.cat((grid_pc, sdf_grid[..., None]), dim=-1).cpu().numpy(), None
+
+    def sdf_fn(self, pts):
+        """numpy [..,3] -> numpy sdf (trainer.py:2066-2070)."""
+        with torch.no_grad():
+            sdf = self.sdf_map(torch.as_tensor(np.asarray(pts), dtype=torch.float32).to(self.device))
+        return sdf.cpu().numpy()
+
+    def grad_fn(self, pts):
+        """numpy [..,3] -> numpy d sdf / d x via K3 (trainer.py:2072-2078)."""
+        pts = torch.as_tensor(np.asarray(pts), dtype=torch.float32).to(self.device).requires_grad_()
+        sdf = self.sdf_map(pts)
+        return fc_map.gradient(pts, sdf).detach().cpu().numpy()
+
+    def render_depth_normals(self, T_WC):
+        """The compute half of latest_frame_vis (trainer.py:1080-1124): coarse depth render on the /16 grid,
+        bilinear up-sampling, +-0.1 m refinement on the /8 grid, camera-frame normals from the SDF gradient.
+        Returns (depth [H/8, W/8], normals_C [H/8, W/8, 3]) on the device."""
+        if getattr(self, "dirs_C_vis", None) is None:
+            self.set_directions()
+        T_WC = torch.as_tensor(T_WC, dtype=torch.float32, device=self.device).reshape(1, 4, 4)
+        with torch.no_grad():
+            pc, z = sample.sample_along_rays(T_WC, self.min_depth, self.max_depth, n_stratified_samples=20,
+                                             n_surf_samples=0, dirs_C=self.dirs_C_vis, gt_depth=None,
+                                             engine=self.sdf_map.engine())
+            depth_vis = render.sdf_render_depth(z, self.sdf_map(pc))
+            depth_up = torch.nn.functional.interpolate(depth_vis.view(1, 1, self.H_vis, self.W_vis),
+                                                       size=[self.H_vis_up, self.W_vis_up], mode='bilinear',
+                                                       align_corners=True).view(-1)
+            pc_up, z_up = sample.sample_along_rays(T_WC, depth_up - 0.1, depth_up + 0.1, n_stratified_samples=12,
+                                                   n_surf_samples=12, dirs_C=self.dirs_C_vis_up,
+                                                   engine=self.sdf_map.engine())
+            depth_vals = render.sdf_render_depth(z_up, self.sdf_map(pc_up))
+        normals = render.render_normals(T_WC, depth_vals[None, ...], self.sdf_map, self.dirs_C_vis_up)
+        return depth_vals.view(self.H_vis_up, self.W_vis_up), normals.view(self.H_vis_up, self.W_vis_up, 3)

@@ -107,3 +107,31 @@ def loss_batch(seed, R, S=27, n_surf=8, min_depth=0.07, dist_behind=0.1):
 
 def subsample(t, stride=97):
     return t.reshape(-1)[::stride].clone()
+
+
+def loss_batch_pc(seed, R, S=27):
+    """loss_batch for the 'pc' (batch-distance) bound: rays share two poses so that surface points of
+    neighbouring rays are the closest ones, and one sample coincides with a surface point (its bounds_pc
+    direction is NaN -> replaced by the ray's normal, trainer.py:823-824)."""
+    batch, noise = loss_batch(seed, R, S=S)
+    g = gen(seed + 7)
+    k = torch.randint(0, 2, (R,), generator=g)
+    T = torch.stack([synthetic_pose(int(i)) for i in k])
+    z = batch["z_vals"].clone()
+    z[1, 3] = batch["depth_sample"][1]                  # sample (1,3) == surface sample of ray 1
+    dirs_W = (T[:, :3, :3] * batch["dirs_C_sample"][:, None, :]).sum(-1)
+    pc = T[:, :3, 3][:, None, :] + dirs_W[:, None, :] * z[:, :, None]
+    pc[1, 3] = pc[1, 0]
+    batch.update(T_WC_sample=T, z_vals=z, dirs_W=dirs_W, pc=pc)
+    return batch, noise
+
+
+def describe(obj):
+    """Nested structure with tensor shapes / dtypes instead of values."""
+    if torch.is_tensor(obj):
+        return ("tensor", tuple(obj.shape), str(obj.dtype))
+    if isinstance(obj, dict):
+        return {k: describe(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [describe(v) for v in obj]
+    return obj

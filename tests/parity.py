@@ -25,10 +25,10 @@ def make_engine(device, cfg, precision="fp32", max_points=32768):
                   transform=cfg.get("transform"), precision=precision, max_points=max_points)
 
 
-def loss_cfg_from(cfg, n_valid):
+def loss_cfg_from(cfg, n_valid, bounds=None, grad_vec=None):
     return make_loss_cfg(cfg["trunc_weight"], cfg["trunc_distance"], cfg["eik_weight"], cfg["eik_apply_dist"],
                          cfg["grad_weight"], cfg.get("orien_loss", False), cfg["loss_type"], cfg["noise_std"],
-                         1.0 / n_valid)
+                         1.0 / n_valid, bounds=bounds, grad_vec=grad_vec)
 
 
 def run_train(engine, sd, batch, noise, cfg, device):
@@ -37,13 +37,17 @@ def run_train(engine, sd, batch, noise, cfg, device):
     engine.zero_grad()
     b = {k: v.to(device=device, dtype=torch.float32) for k, v in batch.items()}
     R, S = b["z_vals"].shape
-    lc = loss_cfg_from(cfg, R * S)
+    pcb = pcv = None
+    if cfg.get("bounds_method", "ray") == "pc":          # N2: bounds from the all-pairs kernel
+        pcb, pcv = engine.bounds_pc(b["pc"], b["z_vals"], b["depth_sample"])
+    lc = loss_cfg_from(cfg, R * S, bounds=pcb, grad_vec=pcv)
     nz = noise.to(device) if (noise is not None and cfg["noise_std"]) else None
     sdf, g, loss_mat, sums = engine.train_fwd_bwd(b["pc"], b["z_vals"], b["depth_sample"], b["dirs_C_sample"],
                                                   b["T_WC_sample"], b["norm_sample"], nz, lc)
     grads = unflatten(engine.export_grads(), sd)
     torch.cuda.synchronize(device)
-    return dict(sdf=sdf.cpu(), g=g.cpu(), loss_mat=loss_mat.cpu(), sums=sums.cpu(), grads=[x.cpu() for x in grads])
+    return dict(sdf=sdf.cpu(), g=g.cpu(), loss_mat=loss_mat.cpu(), sums=sums.cpu(), grads=[x.cpu() for x in grads],
+                pc_bounds=None if pcb is None else pcb.cpu(), pc_vec=None if pcv is None else pcv.cpu())
 
 
 def rel(a, b):

@@ -206,6 +206,71 @@ def test_train_properties_full_size(mode):
     assert P.rel_fro(g1, g2) < max(1e-4, 0.1 * t["gw"])
 
 
+# ---------------------------------------------------------------------------------- N2 ('pc' bound)
+PC_CASES = [("p1", 61, 1.0, None, 48, 0.25, "L1"), ("p2_rigid_L2", 62, 1.5, 9, 32, 0.0, "L2")]
+
+
+@pytest.mark.parametrize("case", PC_CASES, ids=[c[0] for c in PC_CASES])
+def test_bounds_pc_matches_reference_golden(case):
+    """isdfb_bounds_pc against loss.bounds_pc of the unmodified reference (loss.py:56-89), incl. the NaN row."""
+    tag, seed, gain, tr, R, nstd, lt = case
+    gold = load("step_pc.pt")[tag]
+    batch, _ = C.loss_batch_pc(seed + 100, R)
+    eng = _engine(O.default_cfg(), "fp32", max_points=1024)
+    b = {k: v.to(DEV) for k, v in batch.items()}
+    bnd, vec = eng.bounds_pc(b["pc"], b["z_vals"], b["depth_sample"])
+    bnd, vec = bnd.cpu(), vec.cpu()[:, 1:]
+    assert torch.allclose(bnd, gold["bounds"], atol=1e-6, rtol=1e-6)
+    nan_gold = gold["grad_vec"][..., 0].isnan()
+    assert torch.equal(vec[..., 0].isnan(), nan_gold)
+    assert torch.allclose(vec[~nan_gold], gold["grad_vec"][~nan_gold], atol=2e-6)
+
+
+def test_bounds_pc_full_size_properties():
+    """C4-sized batch (20 480 rays x 64 samples vs 20 480 surface points): every bound is attained by a
+    surface point (brute-force check on a slice), |bound| of a surface sample is 0, masked rays are ignored."""
+    R, S = 20480, 64
+    batch, _ = C.loss_batch(301, R, S=S, n_surf=8)
+    b = {k: v.to(DEV) for k, v in batch.items()}
+    eng = _engine(O.default_cfg(), "fp32", max_points=1024)
+    valid = torch.ones(R, dtype=torch.uint8, device=DEV)
+    valid[::7] = 0
+    bnd, vec = eng.bounds_pc(b["pc"], b["z_vals"], b["depth_sample"], ray_valid=valid)
+    keep = valid.bool()
+    assert float(bnd[keep][:, 0].abs().max()) == 0.0            # a surface sample is its own closest point
+    assert float(bnd[~keep].abs().max()) == 0.0
+    surf = b["pc"][keep][:, 0]
+    rows = torch.arange(0, R, 97, device=DEV)
+    rows = rows[keep[rows]]
+    d = (b["pc"][rows][:, :, None, :] - surf[None, None]).norm(dim=-1).min(dim=-1).values
+    assert torch.allclose(bnd[rows].abs(), d, atol=1e-5, rtol=1e-5)
+    n = vec[keep][:, 1:].norm(dim=-1)
+    assert float((n[~n.isnan()] - 1).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", PC_CASES, ids=[c[0] for c in PC_CASES])
+def test_train_step_pc_bound_matches_reference_golden(mode, case):
+    tag, seed, gain, tr, R, nstd, lt = case
+    gold = load("step_pc.pt")[tag]
+    sd = C.golden_weights(seed, gain=gain)
+    cfg = O.default_cfg(noise_std=nstd, loss_type=lt, transform=C.rigid_transform(tr) if tr else None,
+                        bounds_method="pc")
+    batch, noise = C.loss_batch_pc(seed + 100, R)
+    out = P.run_train(_engine(cfg, mode, max_points=1024), sd, batch, noise, cfg, DEV)
+    t = TOL[mode]
+    assert P.rel(out["sdf"], gold["sdf"]) < t["sdf"]
+    assert P.rel(out["g"], gold["grad"]) < t["g"]
+    assert P.rel(out["loss_mat"], gold["total_mat"]) < max(t["loss"], 10 * t["g"] * 0.02)
+    n = out["sdf"].numel()
+    for k, idx in (("sdf_loss", 0), ("grad_loss", 1), ("eikonal_loss", 2), ("total_loss", 3)):
+        ref = gold["losses"][k]
+        assert abs(float(out["sums"][idx]) / n - ref) <= t["loss"] * max(abs(ref), 1e-3), k
+    for name, gr in zip(sd.keys(), out["grads"]):
+        sub = C.subsample(gr) if gr.numel() > 4096 else gr
+        assert P.rel_fro(sub, gold["grad_sub"][name]) < t["gw_small"], name
+
+
 # ---------------------------------------------------------------------------------- K5
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_frame_bins_matches_reference_golden(case):

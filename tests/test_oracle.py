@@ -129,6 +129,39 @@ def test_sweep_formulation_matches_reference(case):
     _check_against_gold(out, gold, sd, 5e-6, 1e-4, 5e-4)
 
 
+PC_CASES = [("p1", 61, 1.0, None, 48, 0.25, "L1"), ("p2_rigid_L2", 62, 1.5, 9, 32, 0.0, "L2")]
+
+
+def _case_pc(tag, seed, gain, tr, R, nstd, lt, dtype=torch.float32):
+    layers, _, _, cfg, sd = _case(tag, seed, gain, tr, R, nstd, lt, dtype)
+    batch, noise = C.loss_batch_pc(seed + 100, R)
+    cfg = dict(cfg, bounds_method="pc")
+    if dtype == torch.float64 and cfg.get("transform") is not None:
+        cfg["transform"] = cfg["transform"].double()
+    return layers, {k: v.to(dtype) for k, v in batch.items()}, noise.to(dtype), cfg, sd
+
+
+@pytest.mark.parametrize("case", PC_CASES, ids=[c[0] for c in PC_CASES])
+def test_bounds_pc_matches_reference(case):
+    """Row N2: the batch-distance bound and its direction field against loss.bounds_pc (loss.py:56-89)."""
+    gold = load("step_pc.pt")[case[0]]
+    _, batch, _, cfg, _ = _case_pc(*case)
+    bnd, vec = O.bounds_pc(batch["pc"], batch["z_vals"], batch["depth_sample"])
+    assert torch.allclose(bnd, gold["bounds"], atol=1e-6, rtol=1e-6)
+    nan_gold = gold["grad_vec"][..., 0].isnan()
+    assert torch.equal(vec[..., 0].isnan(), nan_gold) and int(nan_gold.sum()) == 1
+    assert torch.allclose(vec[~nan_gold], gold["grad_vec"][~nan_gold], atol=2e-6)
+
+
+@pytest.mark.parametrize("case", PC_CASES, ids=[c[0] for c in PC_CASES])
+def test_pc_bound_step_matches_reference(case):
+    gold = load("step_pc.pt")[case[0]]
+    layers, batch, noise, cfg, sd = _case_pc(*case)
+    _check_against_gold(O.step_autograd(layers, batch, cfg, noise), gold, sd, 2e-6, 2e-5, 2e-4)
+    layers, batch, noise, cfg, sd = _case_pc(*case, dtype=torch.float64)
+    _check_against_gold(O.step_sweeps(layers, batch, cfg, noise), gold, sd, 5e-6, 1e-4, 5e-4)
+
+
 def test_sweeps_equal_autograd_fp64():
     layers, batch, noise, cfg, sd = _case("c2", 32, 2.0, 9, 40, 0.04, "L1", dtype=torch.float64)
     cfg = dict(cfg, transform=cfg["transform"].double())
