@@ -195,6 +195,24 @@ int isdfb_adamw_set_step(isdfb_ctx* ctx, int64_t step, void* stream);
 /* ctx-internal gradient buffer (fp32, padded internal layout) for the NCCL all-reduce.     */
 int isdfb_grad_buffer(isdfb_ctx* ctx, float** ptr, int64_t* n_floats);
 
+/* ---- C1 fused: the gradient all-reduce as the flush of the weight-gradient kernel ------------------------
+ * Data-parallel ranks (one process per GPU, keyframes sharded -- SURVEY.md 8e) exchange ONE thing per
+ * step: the packed parameter gradient.  Instead of a separate all-reduce, the caller allocates two
+ * gradient buffers in symmetric memory (same virtual layout on every rank, plus an NVLink-multicast
+ * alias of each) and installs them here; K4 then flushes its gradient tiles with `multimem.red` into the
+ * multicast alias, so every rank's copy receives the sum over ranks inside the NVSwitch while the
+ * kernel is still draining.  Protocol per step n (b = n mod 2), driven by the caller on one stream:
+ *     isdfb_select_grad_buffer(b); K4 (accumulates into buffer b on ALL ranks);
+ *     isdfb_zero_grad_buffer(1-b)  (own copy, for step n+1);  cross-rank barrier;  K6 (reads own copy b).
+ * Buffer 1-b is zeroed BEFORE the barrier, so no rank can add into it for step n+1 before its owner
+ * cleared it.  local*: this rank's buffers; mcast*: their multicast addresses; n_floats >= the size
+ * isdfb_grad_buffer reports.  All four NULL uninstalls.  Tensor-core precisions only.  The reference has no
+ * counterpart (single process, trainer.py:981-982).                                                     */
+int isdfb_set_grad_exchange(isdfb_ctx* ctx, float* local0, float* local1, float* mcast0, float* mcast1,
+                            int64_t n_floats);
+int isdfb_select_grad_buffer(isdfb_ctx* ctx, int32_t which);
+int isdfb_zero_grad_buffer(isdfb_ctx* ctx, int32_t which, void* stream);
+
 /* ---- kernel timing (bench.py roofline) ---------------------------------------------------
  * When enabled, the tensor-core path brackets its two kernels (the fused PE+MLP chain kernel and
  * the weight-gradient kernel) with CUDA events on the launching stream.  isdfb_profile_read

@@ -56,6 +56,9 @@ SIGNATURES = {
     "isdfb_bounds_pc": (C.c_int, [P, P, P, P, P, I64, I32, P, P, P]),
     "isdfb_train_fwd_bwd": (C.c_int, [P, P, P, P, P, P, P, P, P, I64, I32, C.POINTER(LossCfg), P, P, P, P, P]),
     "isdfb_zero_grad": (C.c_int, [P, P]),
+    "isdfb_set_grad_exchange": (C.c_int, [P, P, P, P, P, I64]),
+    "isdfb_select_grad_buffer": (C.c_int, [P, I32]),
+    "isdfb_zero_grad_buffer": (C.c_int, [P, I32, P]),
     "isdfb_export_grads": (C.c_int, [P, P, P]),
     "isdfb_frame_bins": (C.c_int, [P, P, P, P, P, P, I64, I32, I32, I32, I32, I32, P, P, P]),
     "isdfb_adamw": (C.c_int, [P, P, P, P, I64, F, F, F, F, F, F, P]),

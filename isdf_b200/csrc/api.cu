@@ -93,6 +93,7 @@ int isdfb_create(const isdfb_model_cfg* cfg, int device, isdfb_ctx** out) {
   CREATE_CUDA(cudaSetDevice(device));
   CREATE_CUDA(cudaMalloc(&ctx->w_packed, ctx->lay.n_packed * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&ctx->g_packed, ctx->lay.n_packed * sizeof(float)));
+  ctx->g_own = ctx->g_packed;
   CREATE_CUDA(cudaMemset(ctx->w_packed, 0, ctx->lay.n_packed * sizeof(float)));
   CREATE_CUDA(cudaMemset(ctx->g_packed, 0, ctx->lay.n_packed * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&ctx->adam_dev, 64));
@@ -117,7 +118,7 @@ int isdfb_destroy(isdfb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->tc) tc_destroy(ctx);
   if (ctx->w_packed) cudaFree(ctx->w_packed);
-  if (ctx->g_packed) cudaFree(ctx->g_packed);
+  if (ctx->g_own) cudaFree(ctx->g_own);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->adam_dev) cudaFree(ctx->adam_dev);
   delete ctx;
@@ -239,6 +240,47 @@ int isdfb_train_fwd_bwd(isdfb_ctx* ctx, const float* pc, const float* z_vals, co
 int isdfb_zero_grad(isdfb_ctx* ctx, void* stream) {
   ENTER(ctx);
   ISDFB_CUDA_OK(ctx, cudaMemsetAsync(ctx->g_packed, 0, ctx->lay.n_packed * sizeof(float), st));
+  return ISDFB_OK;
+}
+
+int isdfb_set_grad_exchange(isdfb_ctx* ctx, float* local0, float* local1, float* mcast0, float* mcast1,
+                            int64_t n_floats) {
+  if (!ctx) return ISDFB_ERR_ARG;
+  if (!local0 && !local1 && !mcast0 && !mcast1) {          // uninstall
+    ctx->g_xchg = false;
+    ctx->g_packed = ctx->g_own;
+    return ISDFB_OK;
+  }
+  if (!local0 || !local1 || !mcast0 || !mcast1)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_set_grad_exchange: two local buffers and their two multicast addresses are required");
+  if (n_floats < ctx->lay.n_packed)
+    ISDFB_FAIL(ctx, ISDFB_ERR_CAPACITY, "isdfb_set_grad_exchange: buffers hold %lld floats, the packed gradient needs %lld",
+               (long long)n_floats, (long long)ctx->lay.n_packed);
+  if (ctx->cfg.precision == ISDFB_PREC_FP32)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_set_grad_exchange: the fused exchange is implemented by the tensor-core path's "
+                                   "gradient flush; fp32 mode uses the caller's all-reduce on isdfb_grad_buffer");
+  ctx->g_local[0] = local0; ctx->g_local[1] = local1;
+  ctx->g_mc[0] = mcast0; ctx->g_mc[1] = mcast1;
+  ctx->g_sel = 0;
+  ctx->g_xchg = true;
+  ctx->g_packed = local0;
+  return ISDFB_OK;
+}
+
+int isdfb_select_grad_buffer(isdfb_ctx* ctx, int32_t which) {
+  if (!ctx) return ISDFB_ERR_ARG;
+  if (!ctx->g_xchg) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "isdfb_select_grad_buffer: no gradient exchange installed");
+  if (which != 0 && which != 1) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_select_grad_buffer: which must be 0 or 1");
+  ctx->g_sel = which;
+  ctx->g_packed = ctx->g_local[which];
+  return ISDFB_OK;
+}
+
+int isdfb_zero_grad_buffer(isdfb_ctx* ctx, int32_t which, void* stream) {
+  ENTER(ctx);
+  if (!ctx->g_xchg) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "isdfb_zero_grad_buffer: no gradient exchange installed");
+  if (which != 0 && which != 1) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_zero_grad_buffer: which must be 0 or 1");
+  ISDFB_CUDA_OK(ctx, cudaMemsetAsync(ctx->g_local[which], 0, ctx->lay.n_packed * sizeof(float), st));
   return ISDFB_OK;
 }
 

@@ -50,7 +50,13 @@ struct isdfb_ctx {
   PEParams pe;
   int64_t cap;             // max points per chunk (multiple of ISDFB_TILE)
   float* w_packed;         // packed fp32 parameters
-  float* g_packed;         // packed fp32 gradient (same layout)
+  float* g_packed;         // packed fp32 gradient (same layout): the buffer K6 / export read
+  float* g_own;            // the library's own allocation (g_packed points here unless an exchange is installed)
+  // C1 fused: gradient exchange over NVLink multicast (isdfb_set_grad_exchange); two buffers alternate per step
+  float* g_local[2];       // this rank's copies (symmetric memory owned by the caller)
+  float* g_mc[2];          // multicast (NVLS) addresses of the same buffers: a reduction lands in every rank's copy
+  int g_sel;               // buffer the next launches accumulate into / K6 reads
+  bool g_xchg;
   bool weights_ready;
   int64_t launches;
   char err[512];

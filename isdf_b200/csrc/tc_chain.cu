@@ -57,8 +57,10 @@ struct EpiT {                       // per-thread / per-tile constants (thread o
   uint8_t* sig;                     // sigma16 layer 0 + tile + p*16 + (2 jg) 2048
   size_t dwl_stride, aux_stride, sig_stride;
   int p, kcol;                      // kcol = 16 jg
+  int c0;                           // first K chunk of this CTA's rotated order (rot_kstep)
+  int ablate;
 };
-struct EpiOps { uint4 s, b0, b1; };   // side-array operands of one sub-piece
+struct EpiOps { uint4 s, b0, b1, e0, e1; };   // side-array operands of one sub-piece (e0/e1: own embedding values, S2_END)
 struct EpiStepPtrs {                  // per-step pointers (thread offsets included)
   const uint8_t* sigp; uint8_t* sigw;
   const uint8_t *dhi, *dlo;           // delta_l (dW layout) for S3
@@ -67,7 +69,8 @@ struct EpiStepPtrs {                  // per-step pointers (thread offsets inclu
   float* part_out;                    // RAW: partial sums produced
   const float *bias, *wout;
   float* hlast;
-  const float* e32;                   // aux e32 base WITHOUT the column-group offset (tile + p*4)
+  const float* e32;                   // this thread's slice of the fp32 embedding side array (same offsets as aux)
+  int ablate;
 };
 __device__ __forceinline__ uint32_t sub_a(int c, int h) { return (uint32_t)(8 * c + h) * A_LBO; }
 __device__ __forceinline__ uint32_t sub_d(int c, int h) { return (uint32_t)(8 * c + h) * 256u; }
@@ -77,11 +80,11 @@ template <int kPasses>
 __device__ __forceinline__ void put8(const EpiT& T, const float* x, int c, int h, bool to_a, int dwl_arr) {
   uint4 hi, lo;
   if (kPasses == 3) split8(x, hi, lo); else hi = pack8_hi(x);
-  if (to_a) {
+  if (to_a && !(T.ablate & 32)) {
     *reinterpret_cast<uint4*>(T.a_hi + sub_a(c, h)) = hi;
     if (kPasses == 3) *reinterpret_cast<uint4*>(T.a_lo + sub_a(c, h)) = lo;
   }
-  if (dwl_arr >= 0) {
+  if (dwl_arr >= 0 && !(T.ablate & 1)) {
     const size_t off = (size_t)dwl_arr * T.dwl_stride + sub_d(c, h);
     *reinterpret_cast<uint4*>(T.dwl_hi + off) = hi;
     if (kPasses == 3) *reinterpret_cast<uint4*>(T.dwl_lo + off) = lo;
@@ -90,6 +93,7 @@ __device__ __forceinline__ void put8(const EpiT& T, const float* x, int c, int h
 
 template <int EPI, int kPasses>
 __device__ __forceinline__ void epi_load(const EpiStepPtrs& P, bool l_is_cat, int c, int h, EpiOps& o) {
+  if (P.ablate & 8) return;
   if (EPI == EPI_S2 || EPI == EPI_S3 || EPI == EPI_S3_LAST || EPI == EPI_S4)
     o.s = *reinterpret_cast<const uint4*>(P.sigp + sub_a(c, h));
   if (EPI == EPI_S3 || EPI == EPI_S3_LAST) {
@@ -101,21 +105,35 @@ __device__ __forceinline__ void epi_load(const EpiStepPtrs& P, bool l_is_cat, in
   } else if (EPI == EPI_S2_END || ((EPI == EPI_S1 || EPI == EPI_S1_LAST) && l_is_cat)) {
     o.b0 = *reinterpret_cast<const uint4*>(P.part_in + sub_x(c, h));
     o.b1 = *reinterpret_cast<const uint4*>(P.part_in + sub_x(c, h) + 512);
+    if (EPI == EPI_S2_END) {
+      o.e0 = *reinterpret_cast<const uint4*>(P.e32 + sub_x(c, h));
+      o.e1 = *reinterpret_cast<const uint4*>(P.e32 + sub_x(c, h) + 512);
+    }
   }
 }
 
 struct EpiAcc { float raw_acc, gx, gy, gz; };
 
+// Per-CTA rotation of the K order of every product (args.stagger): CTA b walks the four 64-column K chunks
+// starting at chunk (b/4)%4 and the four K steps inside a chunk starting at b%4.  All CTAs stream the SAME
+// weight images from L2 at the same pace; without the rotation the 148 SMs ask the same L2 lines for the same
+// 8 KB block at the same moment and queue behind each other (measured: 12 k cycles per step for the weight
+// ring alone).  The sum over K is order-independent up to fp32 rounding.
+__device__ __forceinline__ int rot_kstep(int ks, int rot) {
+  return ((((ks >> 2) + (rot >> 2)) & 3) << 2) | (((ks & 3) + rot) & 3);
+}
+
 template <int EPI, int kPasses>
 __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, const EpiStepPtrs& P, const EpiOps& o,
-                                        uint32_t d_tmem, int c, int h, int l, bool l_is_cat, bool train, bool store_state,
-                                        bool last_step, float sbar, EpiAcc& acc) {
+                                        float* v /* 8 accumulator columns of this sub-piece */, int c, int h, int l,
+                                        bool l_is_cat, bool train, bool store_state, bool last_step, float sbar,
+                                        EpiAcc& acc) {
   const int k0 = 64 * c + T.kcol + 8 * h;
-  float v[8];
-  tmem_ld8(d_tmem + k0, v);
   if (EPI == EPI_RAW) {
-    st4(P.part_out + sub_x(c, h), v[0], v[1], v[2], v[3]);
-    st4(P.part_out + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
+    if (!(T.ablate & 2)) {
+      st4(P.part_out + sub_x(c, h), v[0], v[1], v[2], v[3]);
+      st4(P.part_out + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
+    }
   } else if (EPI == EPI_S1 || EPI == EPI_S1_LAST) {
     const float4 ba = ld4(P.bias + k0), bb = ld4(P.bias + k0 + 4);
     float z[8] = {v[0] + ba.x, v[1] + ba.y, v[2] + ba.z, v[3] + ba.w, v[4] + bb.x, v[5] + bb.y, v[6] + bb.z, v[7] + bb.w};
@@ -124,15 +142,20 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
       z[4] += __uint_as_float(o.b1.x); z[5] += __uint_as_float(o.b1.y); z[6] += __uint_as_float(o.b1.z); z[7] += __uint_as_float(o.b1.w);
     }
     float hh[8], sg[8];
+    if (T.ablate & 16) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) softplus100_fast(z[t], hh[t], sg[t]);
-    if (store_state) *reinterpret_cast<uint4*>(P.sigw + sub_a(c, h)) = pack_unorm16x8(sg);
+      for (int t = 0; t < 8; ++t) { hh[t] = fmaxf(z[t], 0.f); sg[t] = z[t] > 0.f ? 1.f : 0.f; }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) softplus100_fast(z[t], hh[t], sg[t]);
+    }
+    if (store_state && !(T.ablate & 4)) *reinterpret_cast<uint4*>(P.sigw + sub_a(c, h)) = pack_unorm16x8(sg);
     if (EPI == EPI_S1) {
       put8<kPasses>(T, hh, c, h, true, (train && l + 1 < args.L) ? args.arr_yh + l + 1 : -1);
     } else {
       const float4 wa = ld4(P.wout + k0), wb = ld4(P.wout + k0 + 4);
       const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-      if (train) {
+      if (train && !(T.ablate & 2)) {
         st4(P.hlast + sub_x(c, h), hh[0], hh[1], hh[2], hh[3]);
         st4(P.hlast + sub_x(c, h) + 512, hh[4], hh[5], hh[6], hh[7]);
       }
@@ -150,24 +173,27 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
     for (int t = 0; t < 8; ++t) v[t] *= sg[t];
     put8<kPasses>(T, v, c, h, true, train ? args.arr_xd + l : -1);
   } else if (EPI == EPI_S2_END) {
-    const int half = ISDFB_NDIRS * args.pe.n_freqs;
+    if (T.ablate & 64) { acc.gx += v[0]; return; }
+    // PE Jacobian in the internal column order (tc_common.cuh): columns (2i, 2i+1) = (sin, cos) of pair i, so
+    // d e / d xb = (cos, -sin) is thread-local:  g_xs += D_d 2^f (cos a_sin - sin a_cos);  x y z follow the pairs
+    const int two_half = 2 * ISDFB_NDIRS * args.pe.n_freqs;
     const float a[8] = {v[0] + __uint_as_float(o.b0.x), v[1] + __uint_as_float(o.b0.y), v[2] + __uint_as_float(o.b0.z), v[3] + __uint_as_float(o.b0.w),
                         v[4] + __uint_as_float(o.b1.x), v[5] + __uint_as_float(o.b1.y), v[6] + __uint_as_float(o.b1.z), v[7] + __uint_as_float(o.b1.w)};
+    const float ev[8] = {__uint_as_float(o.e0.x), __uint_as_float(o.e0.y), __uint_as_float(o.e0.z), __uint_as_float(o.e0.w),
+                         __uint_as_float(o.e1.x), __uint_as_float(o.e1.y), __uint_as_float(o.e1.z), __uint_as_float(o.e1.w)};
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < 8; t += 2) {
       const int k = k0 + t;
-      if (k < 3) {
-        if (k == 0) acc.gx += a[t]; else if (k == 1) acc.gy += a[t]; else acc.gz += a[t];
-      } else if (k < args.E) {
-        const bool first = (k - 3) < half;
-        const int km = first ? k + half : k - half;
-        const float mate = P.e32[(km >> 2) * 512 + (km & 3)];
-        // d sin(xb)/d xb = "cos" = e[mate];  d sin(xb+pi/2)/d xb = -sin(xb) = -e[mate]
-        const float w = (first ? mate : -mate) * (float)(1 << args.feat_f[k]) * a[t];
-        const int d = args.feat_d[k];
+      if (k < two_half) {
+        const int pi = k >> 1, d = args.pair_d[pi];
+        const float w = (ev[t + 1] * a[t] - ev[t] * a[t + 1]) * (float)(1 << args.pair_f[pi]);
         acc.gx = fmaf(w, c_ico[d][0], acc.gx);
         acc.gy = fmaf(w, c_ico[d][1], acc.gy);
         acc.gz = fmaf(w, c_ico[d][2], acc.gz);
+      } else if (k == two_half) {
+        acc.gx += a[t]; acc.gy += a[t + 1];
+      } else if (k == two_half + 2) {
+        acc.gz += a[t];
       }
     }
   } else if (EPI == EPI_S3 || EPI == EPI_S3_LAST) {
@@ -191,8 +217,10 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
       v[t] = v[t] * sg[t];                 // abar = dbar * sigma
     }
     if (EPI == EPI_S3) {
-      st4(P.zb2 + sub_x(c, h), zb[0], zb[1], zb[2], zb[3]);
-      st4(P.zb2 + sub_x(c, h) + 512, zb[4], zb[5], zb[6], zb[7]);
+      if (!(T.ablate & 2)) {
+        st4(P.zb2 + sub_x(c, h), zb[0], zb[1], zb[2], zb[3]);
+        st4(P.zb2 + sub_x(c, h) + 512, zb[4], zb[5], zb[6], zb[7]);
+      }
       put8<kPasses>(T, v, c, h, true, (l + 1 < args.L) ? args.arr_ya + l + 1 : -1);
     } else {
       // v_blob = sbar * h_last + abar_last  (for d w_out);  A <- zbar_last = sbar c w_out sigma + zbar2
@@ -221,14 +249,15 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
 }
 
 // one whole step of the epilogue for this thread (8 sub-pieces), operands fetched one sub-piece ahead
-template <int EPI, int kPasses>
+template <int EPI, int kPasses, int kWide>
 __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T, const EpiStepPtrs& P, ChainSmemTail* tail,
                                          uint32_t d_tmem, uint32_t n, int l, bool train, bool store_state, bool last_step,
                                          float sbar, EpiAcc& acc, int lane) {
   const bool l_is_cat = (l == args.ic);
   EpiOps oa, ob;
-  oa.s = oa.b0 = oa.b1 = ob.s = ob.b0 = ob.b1 = make_uint4(0, 0, 0, 0);
-  epi_load<EPI, kPasses>(P, l_is_cat, 0, 0, oa);            // overlaps the tail of this step's MMA
+  oa.s = oa.b0 = oa.b1 = oa.e0 = oa.e1 = make_uint4(0, 0, 0, 0);
+  ob = oa;
+  epi_load<EPI, kPasses>(P, l_is_cat, T.c0, 0, oa);         // overlaps the tail of this step's MMA
   mbar_wait(smem_u32(&tail->d_full[n & 1]), (n >> 1) & 1);
   tc_fence_after();
   if (EPI == EPI_RAW) {
@@ -240,22 +269,58 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
       for (int c = 0; c < 4; ++c) mbar_arrive(smem_u32(&tail->a_ready[c]));
     }
   }
+  if (kWide) {
+    // both 8-column halves of a chunk in one straight-line block: one 16-column TMEM load, then two independent
+    // dependency chains the scheduler can interleave; the side operands of the next chunk are requested as
+    // soon as this chunk's are in registers (a whole chunk ahead)
+    epi_load<EPI, kPasses>(P, l_is_cat, T.c0, 1, ob);
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    epi_load<EPI, kPasses>(P, l_is_cat, c, 1, ob);
-    epi_sub<EPI, kPasses>(args, T, P, oa, d_tmem, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
-    if (c < 3) epi_load<EPI, kPasses>(P, l_is_cat, c + 1, 0, oa);
-    epi_sub<EPI, kPasses>(args, T, P, ob, d_tmem, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
-    if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
+    for (int ci = 0; ci < 4; ++ci) {
+      const int c = (ci + T.c0) & 3;
+      float v[16];
+      tmem_ld16(d_tmem + 64 * c + T.kcol, v);
+      const EpiOps ca = oa, cb = ob;
+      if (ci < 3) {
+        epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 0, oa);
+        epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 1, ob);
+      }
+      epi_sub<EPI, kPasses>(args, T, P, ca, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      epi_sub<EPI, kPasses>(args, T, P, cb, v + 8, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int ci = 0; ci < 4; ++ci) {
+      const int c = (ci + T.c0) & 3;
+      float v[8];
+      if (T.ablate & 128) {           // DEV: barrier hand-off only (measures the MMA / weight-ring pipeline alone)
+        if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
+        }
+        continue;
+      }
+      epi_load<EPI, kPasses>(P, l_is_cat, c, 1, ob);
+      tmem_ld8(d_tmem + 64 * c + T.kcol, v);
+      epi_sub<EPI, kPasses>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      if (ci < 3) epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 0, oa);
+      tmem_ld8(d_tmem + 64 * c + T.kcol + 8, v);
+      epi_sub<EPI, kPasses>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
+      }
     }
   }
   tc_fence_before();
 }
 
-template <int kPasses>
+template <int kPasses, int kWide>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_constant__ TcChainArgs args) {
   using Cfg = ChainCfg<kPasses>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -281,6 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
 
+  const int rot = args.stagger ? (int)(blockIdx.x & 15u) : 0;
   const int my_tiles = (args.n_tiles > (int)blockIdx.x) ? (args.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == EPI_WARPS + 1) {
@@ -322,9 +388,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             mbar_wait(smem_u32(&tail->w_empty[stage]), ph ^ 1);
             const uint32_t bar = smem_u32(&tail->w_full[stage]);
             const uint32_t dst = smem_u32(w_ring + stage * Cfg::kStageBytes);
+            if (args.ablate & 512) { mbar_arrive(bar); continue; }      // DEV: no weight traffic at all
+            const int kse = rot_kstep(ks, rot);
             mbar_arrive_expect_tx(bar, Cfg::kStageBytes);
-            bulk_g2s(dst, img_hi + (size_t)ks * KSTEP_IMG_BYTES, KSTEP_IMG_BYTES, bar);
-            if (kPasses == 3) bulk_g2s(dst + KSTEP_IMG_BYTES, img_lo + (size_t)ks * KSTEP_IMG_BYTES, KSTEP_IMG_BYTES, bar);
+            bulk_g2s(dst, img_hi + (size_t)kse * KSTEP_IMG_BYTES, KSTEP_IMG_BYTES, bar);
+            if (kPasses == 3) bulk_g2s(dst + KSTEP_IMG_BYTES, img_lo + (size_t)kse * KSTEP_IMG_BYTES, KSTEP_IMG_BYTES, bar);
           }
         }
       }
@@ -337,17 +405,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
       for (int s = 0; s < n_steps; ++s, ++n) {
         const uint32_t d_tmem = tmem + (n & 1) * 256;
         for (int ks = 0; ks < N_KSTEPS; ++ks, ++j) {
-          if ((ks & 3) == 0) mbar_wait(smem_u32(&tail->a_ready[ks >> 2]), n & 1);
+          const int kse = rot_kstep(ks, rot);
+          if ((ks & 3) == 0) mbar_wait(smem_u32(&tail->a_ready[kse >> 2]), n & 1);
           const uint32_t stage = j % Cfg::kStages, ph = (j / Cfg::kStages) & 1;
           mbar_wait(smem_u32(&tail->w_full[stage]), ph);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t b_base = smem_u32(w_ring + stage * Cfg::kStageBytes);
-            const uint64_t ah = umma_desc(smem_u32(a_hi) + ks * 2 * A_LBO, A_LBO, 128);
+            const uint64_t ah = umma_desc(smem_u32(a_hi) + kse * 2 * A_LBO, A_LBO, 128);
             const uint64_t bh = umma_desc(b_base, B_LBO, 128);
-            tc_mma_f16(d_tmem, ah, bh, idesc, ks != 0);
-            if (kPasses == 3) {
-              const uint64_t al = umma_desc(smem_u32(a_lo) + ks * 2 * A_LBO, A_LBO, 128);
+            if (!(args.ablate & 256)) tc_mma_f16(d_tmem, ah, bh, idesc, ks != 0);
+            if (kPasses == 3 && !(args.ablate & 256)) {
+              const uint64_t al = umma_desc(smem_u32(a_lo) + kse * 2 * A_LBO, A_LBO, 128);
               const uint64_t bl = umma_desc(b_base + KSTEP_IMG_BYTES, B_LBO, 128);
               tc_mma_f16(d_tmem, al, bh, idesc, 1);
               tc_mma_f16(d_tmem, ah, bl, idesc, 1);
@@ -369,8 +438,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float c_out = args.scale_output;
     const float* Wp = args.w_packed;
-    const int E = args.E;
-    const int half = ISDFB_NDIRS * args.pe.n_freqs;
+    const int two_half = 2 * ISDFB_NDIRS * args.pe.n_freqs;      // internal columns [0, two_half) are (sin, cos) pairs
     const bool train = args.mode == TC_MODE_TRAIN;
     const bool store_state = args.mode != TC_MODE_FWD;
     uint32_t n = 0;
@@ -381,7 +449,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
       const int64_t pl = (int64_t)tile * TC_TILE + p;             // point index inside the chunk
       const bool real = pl < args.n_points;
       EpiT T;
-      T.p = p; T.kcol = 16 * jg;
+      T.p = p; T.kcol = 16 * jg; T.ablate = args.ablate; T.c0 = rot >> 2;
       T.a_hi = a_hi + p * 16 + (2 * jg) * A_LBO;
       T.a_lo = a_lo + p * 16 + (2 * jg) * A_LBO;
       const size_t dthr = (size_t)tile * TC_DWL_TILE_BYTES + (size_t)(p >> 4) * 8192u + (size_t)(p & 15) * 16u + (size_t)(2 * jg) * 256u;
@@ -390,7 +458,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
       T.aux = args.aux + (size_t)tile * TC_TILE_FLOATS + p * 4 + (4 * jg) * 512;
       T.sig = args.sig16 + (size_t)tile * TC_DWL_TILE_BYTES + p * 16 + (2 * jg) * 2048;
       T.dwl_stride = args.dwl_stride; T.aux_stride = args.aux_stride; T.sig_stride = args.sig16_stride;
-      const float* e32_thr = args.aux + (size_t)args.arr_e32 * args.aux_stride + (size_t)tile * TC_TILE_FLOATS + p * 4;
       float* e32_w = T.aux + (size_t)args.arr_e32 * args.aux_stride;
       auto chunk_ready = [&](int c) {
         fence_proxy_async_smem();
@@ -398,6 +465,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
       };
 
+      if (args.dbg_clock && blockIdx.x == 0 && threadIdx.x == 0 && it == 0) args.dbg_clock[120] = clock64();
       // ---------------- PE stage: x -> e (A operand of the first step) ----------------
       float xs[3] = {0.f, 0.f, 0.f};
       if (real) {
@@ -410,21 +478,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         const int k0 = 64 * c + T.kcol + 8 * h;
         float v[8];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
+        for (int jj = 0; jj < 8; jj += 2) {         // internal column order: (sin, cos) pairs, then x y z, then padding
           const int k = k0 + jj;
-          float val = 0.f;
-          if (real && k < E) {
-            if (k < 3) {
-              val = (k == 0) ? xs[0] : ((k == 1) ? xs[1] : xs[2]);
-            } else {
-              const float xb = pe_project(xs, args.feat_d[k]) * (float)(1 << args.feat_f[k]);
-              val = (k - 3 < half) ? sinf(xb) : sinf(__fadd_rn(xb, ISDFB_HALF_PI_F));
+          float va = 0.f, vb = 0.f;
+          if (real) {
+            if (k < two_half) {
+              const int pi = k >> 1;
+              const float xb = pe_project(xs, args.pair_d[pi]) * (float)(1 << args.pair_f[pi]);
+              va = sinf(xb);
+              vb = sinf(__fadd_rn(xb, ISDFB_HALF_PI_F));
+            } else if (k == two_half) {
+              va = xs[0]; vb = xs[1];
+            } else if (k == two_half + 2) {
+              va = xs[2];
             }
           }
-          v[jj] = val;
+          v[jj] = va; v[jj + 1] = vb;
         }
         put8<kPasses>(T, v, c, h, true, train ? args.arr_yh : -1);
-        if (store_state) {
+        if (store_state && !(args.ablate & 2)) {
           st4(e32_w + sub_x(c, h), v[0], v[1], v[2], v[3]);
           st4(e32_w + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
         }
@@ -453,18 +525,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         P.bias = Wp + args.lay_b_off[l];
         P.wout = Wp + args.wout_off;
         P.hlast = T.aux + (size_t)args.arr_hlast * T.aux_stride;
-        P.e32 = e32_thr;
+        P.e32 = e32_w;
+        P.ablate = args.ablate;
         EpiAcc acc = {0.f, 0.f, 0.f, 0.f};
         if (dbg) args.dbg_clock[1 + 2 * s] = clock64();
         switch (epi) {
-          case EPI_RAW:     epi_step<EPI_RAW, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S1:      epi_step<EPI_S1, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S1_LAST: epi_step<EPI_S1_LAST, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S2:      epi_step<EPI_S2, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S2_END:  epi_step<EPI_S2_END, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S3:      epi_step<EPI_S3, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S3_LAST: epi_step<EPI_S3_LAST, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          default:          epi_step<EPI_S4, kPasses>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_RAW:     epi_step<EPI_RAW, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S1:      epi_step<EPI_S1, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S1_LAST: epi_step<EPI_S1_LAST, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S2:      epi_step<EPI_S2, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S2_END:  epi_step<EPI_S2_END, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S3:      epi_step<EPI_S3, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S3_LAST: epi_step<EPI_S3_LAST, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          default:          epi_step<EPI_S4, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
         }
 
         if (dbg) args.dbg_clock[2 + 2 * s] = clock64();
@@ -529,26 +602,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             const float4 b4 = ld4(bcast + p * 4);
             sbar = b4.x; u3[0] = b4.y; u3[1] = b4.z; u3[2] = b4.w;
             // abar_e -> A operand of S3 (second pass over this thread's columns)
+            float4 ea = ld4(e32_w + sub_x(0, 0)), eb = ld4(e32_w + sub_x(0, 0) + 512);
 #pragma unroll 1
             for (int i = 0; i < 8; ++i) {
               const int c = i >> 1, h = i & 1;
               const int k0 = 64 * c + T.kcol + 8 * h;
+              const float ev[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+              if (i < 7) {                       // own embedding values of the next sub-piece, one ahead
+                const int cn = (i + 1) >> 1, hn = (i + 1) & 1;
+                ea = ld4(e32_w + sub_x(cn, hn));
+                eb = ld4(e32_w + sub_x(cn, hn) + 512);
+              }
               float v[8];
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
+              for (int jj = 0; jj < 8; jj += 2) {
                 const int k = k0 + jj;
-                float val = 0.f;
-                if (k < 3) {
-                  val = (k == 0) ? u3[0] : ((k == 1) ? u3[1] : u3[2]);
-                } else if (k < E) {
-                  const int d = args.feat_d[k];
-                  const float ud = (u3[0] * c_ico[d][0] + u3[1] * c_ico[d][1] + u3[2] * c_ico[d][2]) * (float)(1 << args.feat_f[k]);
-                  const bool first = (k - 3) < half;
-                  const int km = first ? k + half : k - half;
-                  const float mate = e32_thr[(km >> 2) * 512 + (km & 3)];
-                  val = first ? ud * mate : -ud * mate;
+                float va = 0.f, vb = 0.f;
+                if (args.ablate & 64) {
+                  va = u3[0];
+                } else if (k < two_half) {       // abar_e = (u . D_d) 2^f (cos, -sin)
+                  const int pi = k >> 1, d = args.pair_d[pi];
+                  const float ud = (u3[0] * c_ico[d][0] + u3[1] * c_ico[d][1] + u3[2] * c_ico[d][2]) * (float)(1 << args.pair_f[pi]);
+                  va = ud * ev[jj + 1];
+                  vb = -ud * ev[jj];
+                } else if (k == two_half) {
+                  va = u3[0]; vb = u3[1];
+                } else if (k == two_half + 2) {
+                  va = u3[2];
                 }
-                v[jj] = val;
+                v[jj] = va; v[jj + 1] = vb;
               }
               put8<kPasses>(T, v, c, h, true, args.arr_ya);
               if (h) chunk_ready(c);
@@ -572,7 +654,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         atomicAdd(args.loss_sums + 1, lsum1);
         atomicAdd(args.loss_sums + 2, lsum2);
         atomicAdd(args.loss_sums + 3, lsum3);
-        atomicAdd(args.g_packed + args.bout_off, c_out * sbsum);     // d b_out = c * sum sbar
+        grad_add(args.g_packed + args.bout_off, c_out * sbsum, args.g_mc);     // d b_out = c * sum sbar
       }
     }
   }
@@ -584,9 +666,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
 
 int tc_chain_launch(isdfb_ctx* ctx, const TcChainArgs& args, int passes, int grid, cudaStream_t st) {
   if (passes == 3) {
-    tc_chain_kernel<3><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
+    if (args.wide) tc_chain_kernel<3, 1><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
+    else tc_chain_kernel<3, 0><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
   } else {
-    tc_chain_kernel<1><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
+    if (args.wide) tc_chain_kernel<1, 1><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
+    else tc_chain_kernel<1, 0><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
   }
   ISDFB_LAUNCHED(ctx);
   ISDFB_CUDA_OK(ctx, cudaGetLastError());
@@ -594,7 +678,9 @@ int tc_chain_launch(isdfb_ctx* ctx, const TcChainArgs& args, int passes, int gri
 }
 
 int tc_chain_init(isdfb_ctx* ctx) {
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
   return ISDFB_OK;
 }

@@ -20,6 +20,11 @@ struct TcChainArgs {
   int32_t n_tiles;           // tiles processed by this launch ...
   int32_t tile0;             // ... starting at this tile of the chunk
   int32_t prefetch;          // 1: bulk-prefetch the next step's side arrays into L2 (producer warp)
+  int32_t stagger;           // 1: per-CTA rotation of the K order (rot_kstep) against L2 hot-spotting on the weights
+  int32_t wide;              // 1: epilogue variant with 16-column TMEM loads (two interleaved chains per chunk)
+  int32_t ablate;            // DEV ONLY (env ISDFB_ABLATE, results invalid): 1 no dW-layout stores, 2 no aux stores,
+                             // 4 no sigma stores, 8 no side loads, 16 relu instead of softplus, 32 no A-image stores,
+                             // 64 no PE-Jacobian / abar_e math -- timing ablations for profiles/
   int64_t n_points;          // real points in this chunk
   int64_t p0;                // global index of the chunk's first point (sample index r*S+j)
   PEParams pe;
@@ -40,6 +45,7 @@ struct TcChainArgs {
   float* loss_mat;           // GLOBAL [R*S]
   float* loss_sums;          // [4]
   float* g_packed;           // packed gradient (d b_out is accumulated by the chain kernel)
+  int32_t g_mc;              // 1: g_packed is a multicast address (multimem.red, see grad_add)
   // per-tile side state
   float* aux;                // fp32 arrays [arr][tile][256*128], aux layout
   size_t aux_stride;         // floats between arrays
@@ -50,7 +56,7 @@ struct TcChainArgs {
   int32_t arr_zb2, arr_part, arr_e32, arr_hlast;            // aux array indices
   int32_t arr_yh, arr_ya, arr_xd, arr_xz, arr_v;            // dW-layout array indices
   long long* dbg_clock;                                     // optional: per-step timeline of CTA 0 (tests)
-  uint8_t feat_d[TC_H], feat_f[TC_H];                       // PE column -> (direction, octave)
+  uint8_t pair_d[TC_H / 2], pair_f[TC_H / 2];               // internal PE column pair -> (direction, octave)
 };
 
 int tc_chain_launch(isdfb_ctx* ctx, const TcChainArgs& args, int passes, int grid, cudaStream_t st);

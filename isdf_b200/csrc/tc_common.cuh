@@ -27,6 +27,20 @@ __host__ __device__ __forceinline__ uint32_t dwl_off_bytes(uint32_t f, uint32_t 
 }
 #define TC_DWL_TILE_BYTES 65536u
 
+// (4) INTERNAL embedding column order of the tensor-core path.  The reference lays the embedding out as
+//     [x y z | sin(xb_0..) | sin(xb_0.. + pi/2)] (embedding.py:104-110), which puts the sin / cos "mates" of one
+//     (direction, octave) pair `half` columns apart.  Inside the chain kernel a thread owns 8 consecutive
+//     columns, so the columns are permuted to [sin_0 cos_0 sin_1 cos_1 ... | x y z | pad]: both mates, which
+//     the PE Jacobian (S2) and its adjoint (S3) combine, are thread-local.  Only the weight images of the
+//     two units fed by the embedding (tc_pack.cu) and the flush of their gradients (tc_dw.cu) see the
+//     permutation; the packed fp32 parameters and gradients stay in the reference's order.
+__host__ __device__ __forceinline__ int pe_nat_col(int c, int half) {     // internal column -> reference column
+  if (half <= 0) return c;
+  if (c < 2 * half) return 3 + (c >> 1) + (c & 1) * half;
+  if (c < 2 * half + 3) return c - 2 * half;
+  return c;
+}
+
 // ---- misc PTX ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -182,6 +196,19 @@ __device__ __forceinline__ void softplus100_fast(float z, float& h, float& sig) 
   h = fmaf(lg2_approx(u), 0.0069314718055994531f, fmaxf(z, 0.f));   // + ln(2)/100 * log2(1+t)
 }
 
+// ---- gradient accumulation -------------------------------------------------------------------------
+// Single GPU: red.global.add into the packed gradient.  Data parallel with an exchange installed
+// (isdfb_set_grad_exchange): `p` is a MULTICAST address and multimem.red adds the value into every rank's
+// copy inside the NVSwitch -- the all-reduce of the reference-free data-parallel design is the flush itself.
+__device__ __forceinline__ void grad_add(float* p, float v, int mc) {
+  if (mc) asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+  else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void grad_add4(float* p, float a, float b, float c, float d, int mc) {
+  if (mc) asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- descriptors --------------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4   [16,30) LBO>>4   [32,46) SBO>>4   [46,48) version=1   [61,64) layout=0
@@ -244,5 +271,6 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* x) {
 struct TcUnit {
   int64_t w_off;      // offset of the fp32 [256][256] block in the packed parameter buffer
   int32_t ld;         // its leading dimension
+  int32_t perm_half;  // > 0: the unit's input axis is the embedding -> internal column order (pe_nat_col)
 };
 #define TC_MAX_UNITS (ISDFB_MAX_HIDDEN_LAYERS + 1)

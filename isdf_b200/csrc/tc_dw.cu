@@ -139,17 +139,21 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const TcDwArgs arg
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         tmem_ld32(tmem + lane_addr + c * 32, v);
+        if (job.perm_half > 0) {     // embedding-fed unit: internal column order -> the reference's (pe_nat_col)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            grad_add(grow + pe_nat_col(c * 32 + i, job.perm_half), v[i], args.g_mc);
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(grow + c * 32 + i * 4), "f"(v[i * 4]),
-                       "f"(v[i * 4 + 1]), "f"(v[i * 4 + 2]), "f"(v[i * 4 + 3])
-                       : "memory");
+          grad_add4(grow + c * 32 + i * 4, v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3], args.g_mc);
       }
     }
     if (has_db || has_dw) {
       tmem_ld32(tmem + lane_addr + 256, v);
-      if (has_db) atomicAdd(args.g_packed + job.db_off + row, v[0]);
-      if (has_dw) atomicAdd(args.g_packed + args.wout_off + row, args.scale_output * v[16]);
+      if (has_db) grad_add(args.g_packed + job.db_off + row, v[0], args.g_mc);
+      if (has_dw) grad_add(args.g_packed + args.wout_off + row, args.scale_output * v[16], args.g_mc);
     }
     tc_fence_before();
   }

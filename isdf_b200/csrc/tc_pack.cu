@@ -11,8 +11,14 @@ __global__ void tc_pack_kernel(const float* __restrict__ packed, TcUnitTable uni
   const int n = idx >> 5, k8 = idx & 31;
   const float* W = packed + units.u[unit].w_off;
   const int ld = units.u[unit].ld;
+  const int ph = units.u[unit].perm_half;
   float x[8];
-  if (orient == 0) {                // B[n = out][k = in]
+  if (ph > 0) {                     // input axis = embedding: gather the reference columns in internal order
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      x[i] = (orient == 0) ? W[(size_t)n * ld + pe_nat_col(k8 * 8 + i, ph)]      // B[n = out][k = in(internal)]
+                           : W[(size_t)(k8 * 8 + i) * ld + pe_nat_col(n, ph)];   // B[n = in(internal)][k = out]
+  } else if (orient == 0) {         // B[n = out][k = in]
     const float4 a = *reinterpret_cast<const float4*>(W + (size_t)n * ld + k8 * 8);
     const float4 b = *reinterpret_cast<const float4*>(W + (size_t)n * ld + k8 * 8 + 4);
     x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;

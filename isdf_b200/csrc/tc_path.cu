@@ -63,9 +63,14 @@ int tc_create(isdfb_ctx* ctx) {
   ISDFB_CUDA_OK(ctx, cudaEventCreateWithFlags(&tc->ev_fork, cudaEventDisableTiming));
   ISDFB_CUDA_OK(ctx, cudaEventCreateWithFlags(&tc->ev_join, cudaEventDisableTiming));
   tc->n_units = L + 1;
-  for (int l = 0; l < L; ++l) { tc->units.u[l].w_off = lay.layer[l].w_off; tc->units.u[l].ld = lay.layer[l].k0; }
+  const int pe_half = ISDFB_NDIRS * lay.n_freqs;
+  for (int l = 0; l < L; ++l) {
+    tc->units.u[l].w_off = lay.layer[l].w_off; tc->units.u[l].ld = lay.layer[l].k0;
+    tc->units.u[l].perm_half = (l == 0) ? pe_half : 0;
+  }
   tc->units.u[L].w_off = lay.layer[ic].we_off;
   tc->units.u[L].ld = lay.Ep;
+  tc->units.u[L].perm_half = pe_half;
   tc->tiles_cap = ctx->cap / TC_TILE;
   tc->n_aux = L + 5;
   tc->n_dwl = 4 * L + 1;
@@ -87,6 +92,9 @@ int tc_create(isdfb_ctx* ctx) {
     build_program(lay, mode, a);
     a.mode = mode; a.L = L; a.ic = ic; a.E = lay.E;
     a.prefetch = getenv("ISDFB_NO_PREFETCH") ? 0 : 1;
+    a.stagger = getenv("ISDFB_STAGGER") ? atoi(getenv("ISDFB_STAGGER")) : 1;
+    a.wide = getenv("ISDFB_EPI_WIDE") ? atoi(getenv("ISDFB_EPI_WIDE")) : 0;
+    a.ablate = getenv("ISDFB_ABLATE") ? atoi(getenv("ISDFB_ABLATE")) : 0;
     a.dbg_clock = tc->dbg_clock;
     a.pe = ctx->pe;
     a.scale_output = ctx->cfg.scale_output;
@@ -99,13 +107,9 @@ int tc_create(isdfb_ctx* ctx) {
     a.dwl_hi = tc->dwl_hi; a.dwl_lo = tc->dwl_lo; a.dwl_stride = tc->dwl_stride;
     a.sig16 = tc->sig16; a.sig16_stride = tc->dwl_stride;
     a.arr_zb2 = 0; a.arr_part = L; a.arr_e32 = L + 3; a.arr_hlast = L + 4;
-    for (int k = 0; k < TC_H; ++k) {
-      int q = k - 3;
-      const int half = ISDFB_NDIRS * lay.n_freqs;
-      if (k < 3 || k >= lay.E) { a.feat_d[k] = 0; a.feat_f[k] = 0; continue; }
-      if (q >= half) q -= half;
-      a.feat_d[k] = (uint8_t)(q / lay.n_freqs);
-      a.feat_f[k] = (uint8_t)(q % lay.n_freqs);
+    for (int i = 0; i < TC_H / 2; ++i) {      // pair i = (direction, octave) of internal columns 2i, 2i+1
+      a.pair_d[i] = (uint8_t)(i < pe_half ? i / lay.n_freqs : 0);
+      a.pair_f[i] = (uint8_t)(i < pe_half ? i % lay.n_freqs : 0);
     }
     a.arr_yh = 0; a.arr_ya = L; a.arr_xd = 2 * L; a.arr_xz = 3 * L; a.arr_v = 4 * L;
   }
@@ -118,6 +122,7 @@ int tc_create(isdfb_ctx* ctx) {
       TcDwJob& j = d.jobs[d.n_jobs++];
       j.half = half;
       j.ld = TC_H;
+      j.perm_half = (u == 0 || u == L) ? pe_half : 0;
       if (u < L) {
         j.g_off = lay.layer[u].w_off;
         j.db_off = lay.layer[u].b_off;
@@ -205,9 +210,13 @@ int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* 
     a.ray_valid = ray_valid;
     a.loss_mat = loss_mat;
     a.loss_sums = loss_sums;
+    a.g_packed = ctx->g_xchg ? ctx->g_mc[ctx->g_sel] : ctx->g_packed;
+    a.g_mc = ctx->g_xchg ? 1 : 0;
     const int total_tiles = a.n_tiles;
     const int pi = prof_begin(tc, st);
     TcDwArgs d = tc->dw;
+    d.g_packed = a.g_packed;
+    d.g_mc = a.g_mc;
     int rc;
     if (total_tiles > tc->num_sms && total_tiles < 2 * tc->num_sms && !tc->profiling && !getenv("ISDFB_NO_OVERLAP")) {
       // two waves: the weight gradients of wave 1 run on a side stream underneath the (partial) wave 2
@@ -255,7 +264,7 @@ extern "C" int isdfb_debug_buffers(isdfb_ctx* ctx, float** aux, int64_t* aux_str
     long long h[128];
     cudaMemcpy(h, tc->dbg_clock, sizeof(h), cudaMemcpyDeviceToHost);
     const int ns = tc->proto[TC_MODE_TRAIN].n_steps;
-    printf("[isdfb] CTA0 tile0 timeline (cycles): PE_end=0");
+    printf("[isdfb] CTA0 tile0 timeline (cycles): PE took %lld; PE_end=0", h[0] - h[120]);
     for (int s = 0; s < ns; ++s) printf(" | s%d epi%d wait_end=%lld epi_end=%lld", s, tc->proto[TC_MODE_TRAIN].steps[s].epi, h[1 + 2 * s] - h[0], h[2 + 2 * s] - h[0]);
     printf("\n");
   }

@@ -14,6 +14,7 @@ struct TcDwJob {
   int64_t g_off;           // packed-gradient offset of the unit's [256][ld] block
   int32_t ld;
   int64_t db_off;          // packed-gradient offset of the bias (or -1)
+  int32_t perm_half;       // > 0: gradient columns are in the internal embedding order (pe_nat_col)
 };
 #define TC_MAX_JOBS (2 * TC_MAX_UNITS)
 
@@ -24,6 +25,7 @@ struct TcDwArgs {
   const uint8_t *dwl_hi, *dwl_lo;
   size_t dwl_stride;
   float* g_packed;
+  int32_t g_mc;            // 1: g_packed is a multicast address
   int64_t wout_off;
   float scale_output;
 };

@@ -42,6 +42,44 @@ class _Growable:
         return None if self.buf is None else self.buf[:self.n]
 
 
+class _LazyRows:
+    """Host (numpy) rows kept by reference; the [n, ...] batch is materialised only when somebody reads it
+    (the drivers read im_batch_np / depth_batch_np / T_WC_batch_np for visualisation, never on the step)."""
+
+    def __init__(self, wrap=None):
+        self.rows = [] if wrap is None else [wrap]
+        self._cat = wrap
+
+    def append(self, rows):
+        self.rows.append(rows)
+        self._cat = None
+
+    def replace_last(self, rows):
+        last = self.rows[-1]
+        if last.shape[0] == 1:
+            self.rows[-1] = rows[:1]
+        else:
+            self.rows[-1] = last[:-1]
+            self.rows.append(rows[:1])
+        self._cat = None
+
+    @property
+    def n(self):
+        return sum(r.shape[0] for r in self.rows)
+
+    @property
+    def view(self):
+        if self._cat is None:
+            self._cat = self.rows[0] if len(self.rows) == 1 else np.concatenate(self.rows)
+            self.rows = [self._cat]
+        return self._cat
+
+
+def _holder(rows):
+    big = isinstance(rows, np.ndarray) and rows.ndim >= 3
+    return _LazyRows(wrap=rows) if big else _Growable(wrap=rows)
+
+
 class FrameData:
     def __init__(self, frame_id=None, im_batch=None, im_batch_np=None, depth_batch=None, depth_batch_np=None,
                  T_WC_batch=None, T_WC_batch_np=None, normal_batch=None, frame_avg_losses=None, T_WC_track=None,
@@ -62,7 +100,7 @@ class FrameData:
     def __setattr__(self, name, value):
         if name in _FIELDS:
             if value is not None:
-                self._store[name] = _Growable(wrap=value)
+                self._store[name] = _holder(value)
             else:
                 self._store.pop(name, None)
         else:
@@ -73,7 +111,7 @@ class FrameData:
             return
         g = self._store.get(name)
         if g is None:       # first rows are adopted, not copied (the reference assigns them too, data_util.py:52-60)
-            self._store[name] = _Growable(wrap=rows)
+            self._store[name] = _holder(rows)
         elif replace:
             g.replace_last(rows)
         else:

@@ -215,6 +215,18 @@ class Engine:
     def zero_grad(self):
         self._ck(self.lib.isdfb_zero_grad(self._ctx, self._stream()))
 
+    # ---- C1 fused (gradient exchange over NVLink multicast) ------------------
+    def set_grad_exchange(self, local0, local1, mcast0, mcast1, n_floats):
+        """Install two symmetric-memory gradient buffers (raw addresses) and their multicast aliases."""
+        self._ck(self.lib.isdfb_set_grad_exchange(self._ctx, C.c_void_p(local0), C.c_void_p(local1), C.c_void_p(mcast0),
+                                                  C.c_void_p(mcast1), int(n_floats)))
+
+    def select_grad_buffer(self, which):
+        self._ck(self.lib.isdfb_select_grad_buffer(self._ctx, int(which)))
+
+    def zero_grad_buffer(self, which):
+        self._ck(self.lib.isdfb_zero_grad_buffer(self._ctx, int(which), self._stream()))
+
     def export_grads(self, out=None):
         if out is None:
             out = torch.empty(self.n_params, dtype=torch.float32, device=self.device)

@@ -136,6 +136,12 @@ class Trainer:
         self._loss_host = None
         self._stage = None
         self.dist_world, self.dist_rank = parallel.world()
+        # data-parallel gradient exchange: "multicast" = fused into the K4 flush over NVLink multicast,
+        # "nccl" = one ncclAllReduce, "auto" = multicast when every rank can set it up
+        self.grad_exchange_mode = b200.get("grad_exchange", os.environ.get("ISDFB_GRAD_EXCHANGE", "auto"))
+        self._xchg = None
+        self._xchg_tried = False
+        self._nccl_in_graph = None
 
         self.frames = FrameData()
         self.set_params()
@@ -353,8 +359,10 @@ class Trainer:
                     self._stage_evt = torch.cuda.Event()
                 else:
                     self._stage_evt.synchronize()       # previous async copy must have left the staging buffer
-                self._stage[0].copy_(torch.from_numpy(np.ascontiguousarray(depth_np, dtype=np.float32)))
-                self._stage[1].copy_(torch.from_numpy(np.ascontiguousarray(T_np, dtype=np.float32)))
+                # plain memcpy into the pinned staging buffers (torch's CPU copy_ fans a 3 MB copy out over every
+                # host thread and is ~10x slower here)
+                np.copyto(self._stage[0].numpy(), depth_np, casting="same_kind")
+                np.copyto(self._stage[1].numpy(), T_np, casting="same_kind")
                 depth = self._stage[0].to(self.device, non_blocking=True)
                 T = self._stage[1].to(self.device, non_blocking=True)
                 self._stage_evt.record()
@@ -484,7 +492,7 @@ class Trainer:
                 "norm_sample": norm_s, "binary_masks": None, "ray_valid": ray_valid, "n_frames": n_frames}
 
     # ---- fused forward / loss / backward (trainer.py:768-868 + 981) --------------------------
-    def sdf_eval_and_loss(self, sample_pts, do_avg_loss=True):
+    def sdf_eval_and_loss(self, sample_pts, do_avg_loss=True, zero_grad=True):
         """K4 (+K5).  Returns (total_loss, losses, loss_approx, frame_avg_loss) like the reference;
         the parameter gradient of total_loss is left in the engine's gradient buffer (the fused
         kernel already did the double back-prop), so no .backward() follows."""
@@ -513,7 +521,8 @@ class Trainer:
                            self.grad_weight, self.orien_loss, self.loss_type, self.noise_std or 0.0, inv_count,
                            inv_count_dev=inv_dev, bounds=pc_bounds, grad_vec=pc_vec)
         self._loss_sums.zero_()
-        eng.zero_grad()
+        if zero_grad:
+            eng.zero_grad()
         sdf, _, loss_mat, sums = eng.train_fwd_bwd(pc, sample_pts["z_vals"], sample_pts["depth_sample"],
                                                    sample_pts["dirs_C_sample"], sample_pts["T_WC_sample"],
                                                    sample_pts["norm_sample"] if self.do_normal else None, noise, lc,
@@ -552,7 +561,7 @@ class Trainer:
         return total_loss, losses, loss_approx, frame_avg_loss
 
     # ---- one optimisation step (trainer.py:951-1016) -----------------------------------------
-    def _step_front(self):
+    def _step_front(self, zero_grad=True):
         """Everything up to and including the fused forward/backward (gradient left in the engine)."""
         depth_batch = self.frames.depth_batch
         T_WC_batch = self.frames.T_WC_batch
@@ -567,16 +576,42 @@ class Trainer:
         idx_t = idxs if torch.is_tensor(idxs) else torch.as_tensor(idxs, device=self.device, dtype=torch.int64)
         sample_pts = self.sample_points(depth_batch, T_WC_batch, norm_batch=norm_batch, frame_map=idx_t)
         self.active_pixels = {k: sample_pts[k] for k in ("indices_b", "indices_h", "indices_w")}
-        total_loss, losses, active_loss_approx, frame_avg_loss = self.sdf_eval_and_loss(sample_pts, do_avg_loss=True)
+        total_loss, losses, active_loss_approx, frame_avg_loss = self.sdf_eval_and_loss(sample_pts, do_avg_loss=True,
+                                                                                        zero_grad=zero_grad)
         self.frames.frame_avg_losses[idx_t] = frame_avg_loss
         return losses
 
     def _allreduce(self):
-        """C1: the only collective -- sum of the packed gradient over the data-parallel ranks."""
+        """C1 (NCCL form): the only collective -- sum of the packed gradient over the data-parallel ranks."""
         if self.dist_world > 1:
             parallel.allreduce_sum_(self.sdf_map.engine().grad_buffer())
 
+    def _setup_exchange(self):
+        """Once, collectively: install the multicast gradient exchange when every rank can (else NCCL)."""
+        if self._xchg_tried or self.dist_world == 1:
+            return
+        self._xchg_tried = True
+        if self.grad_exchange_mode == "nccl" or self.precision == "fp32":
+            return
+        self._xchg, err = parallel.try_grad_exchange(self.sdf_map.engine(), self.device)
+        if self._xchg is None and self.grad_exchange_mode == "multicast":
+            raise RuntimeError("grad_exchange='multicast' requested but unavailable: %r" % (err,))
+        if self.dist_rank == 0:
+            print("isdf_b200: gradient exchange = %s" % ("NVLink multicast fused into K4" if self._xchg else
+                                                         "NCCL all-reduce (%r)" % (err,)))
+
     def _step_body(self):
+        self._setup_exchange()
+        if self._xchg is not None:
+            # C1 fused: K4 reduces into buffer b on every rank; clear the other buffer, then one barrier
+            eng, b = self.sdf_map.engine(), self._xchg.parity
+            eng.select_grad_buffer(b)
+            losses = self._step_front(zero_grad=False)
+            eng.zero_grad_buffer(1 - b)
+            self._xchg.barrier()
+            self.optimiser.step(grad_scale=1.0 / self.dist_world)
+            self._xchg.parity = 1 - b
+            return losses
         losses = self._step_front()
         self._allreduce()
         self.optimiser.step(grad_scale=1.0 / self.dist_world)
@@ -597,26 +632,49 @@ class Trainer:
                 tuple([p._version for p in self._plist]))
 
     def _step_graphed(self):
-        """fast mode: the step as CUDA-graph launches -- one graph on a single GPU; with data parallelism
-        two graphs (RNG+K1+K4+K5 | K6) around the eager NCCL all-reduce.  Re-captured whenever the keyframe
-        buffer changes shape or address (a new keyframe)."""
+        """fast mode: the whole step (torch RNG kernels, K1, K4, K5, [exchange], K6) as ONE CUDA-graph launch.
+        Data parallel: with the multicast exchange the barrier is a graph node too and the two buffer parities
+        are two graphs; with NCCL the all-reduce is captured into the graph when the runtime allows it,
+        otherwise the step is two graphs around an eager all-reduce.  Re-captured whenever the keyframe buffer
+        changes shape or address (a new keyframe)."""
+        self._setup_exchange()
+        par = self._xchg.parity if self._xchg is not None else 0
         key = self._graph_key()
-        g = self._graph
+        graphs = self._graph if isinstance(self._graph, dict) else {}
+        g = graphs.get(par)
         if g is not None and g[0] == key:
             g[1].replay()
             if g[3] is not None:
                 self._allreduce()
                 g[3].replay()
+            if self._xchg is not None:
+                self._xchg.parity = 1 - par
             return g[2]
-        if self._graph_seen != key:                 # first step with this buffer layout runs eagerly
-            self._graph_seen = key
-            self._graph = None
+        seen = self._graph_seen if isinstance(self._graph_seen, dict) else {}
+        if seen.get(par) != key:                    # first step with this buffer layout (and parity) runs eagerly
+            seen[par] = key
+            self._graph_seen = seen
+            graphs.pop(par, None)
+            self._graph = graphs
             return self._step_body()
         torch.cuda.synchronize(self.device)
-        front, back = torch.cuda.CUDAGraph(), None
-        if self.dist_world == 1:
-            with torch.cuda.graph(front):
+        front, back, losses = torch.cuda.CUDAGraph(), None, None
+        single = self.dist_world == 1 or self._xchg is not None
+        if not single and self._nccl_in_graph is not False:
+            try:                                    # NCCL all-reduce as a node of the one graph
+                with torch.cuda.graph(front, capture_error_mode="thread_local"):
+                    losses = self._step_body()
+                self._nccl_in_graph = single = True
+            except Exception:   # noqa: BLE001
+                self._nccl_in_graph = False
+                torch.cuda.synchronize(self.device)
+                front = torch.cuda.CUDAGraph()
+        elif single:
+            with torch.cuda.graph(front, capture_error_mode="thread_local"):
                 losses = self._step_body()
+            if self._xchg is not None:
+                self._xchg.parity = par             # capture ran the host side of _step_body: undo its parity flip
+        if single:
             front.replay()                          # capture does not execute
         else:
             with torch.cuda.graph(front):
@@ -627,7 +685,10 @@ class Trainer:
             with torch.cuda.graph(back):
                 self.optimiser.step(grad_scale=1.0 / self.dist_world)
             back.replay()
-        self._graph = (key, front, losses, back)
+        if self._xchg is not None:
+            self._xchg.parity = 1 - par
+        graphs[par] = (key, front, losses, back)
+        self._graph = graphs
         return losses
 
     def step(self, sync=True):

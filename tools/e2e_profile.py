@@ -25,7 +25,16 @@ tr.scene_dataset.cache_frames = True
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 for i in range(0, n, 10):
     _ = tr.scene_dataset[100 + i // 10]
-T = dict(get=0.0, add=0.0, step=0.0, read=0.0)
+T = dict(get=0.0, add=0.0, step=0.0, read=0.0, ev=0.0)
+# variants of the bare step loop (no ingest)
+for name, fn in (("replay only, one sync at the end", lambda: tr.step(sync=False)),
+                 ("step(sync=False) + cuda.synchronize()", lambda: (tr.step(sync=False), torch.cuda.synchronize())),
+                 ("step() [events + sync]", lambda: tr.step())):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(200):
+        fn()
+    torch.cuda.synchronize()
+    print("%-45s %.3f ms/step" % (name, 1e3 * (time.perf_counter() - t0) / 200))
 nf = 100
 t_all = time.perf_counter()
 for i in range(n):
@@ -33,7 +42,7 @@ for i in range(n):
         t0 = time.perf_counter(); fd = tr.get_data([nf]); nf += 1
         t1 = time.perf_counter(); tr.last_is_keyframe = False; tr.add_data(fd)
         t2 = time.perf_counter(); T["get"] += t1 - t0; T["add"] += t2 - t1
-    t0 = time.perf_counter(); losses, _ = tr.step(sync=False)
+    t0 = time.perf_counter(); losses, ev_ms = tr.step(); T["ev"] += ev_ms / 1e3
     t1 = time.perf_counter(); v = float(losses["total_loss"])
     t2 = time.perf_counter(); T["step"] += t1 - t0; T["read"] += t2 - t1
 torch.cuda.synchronize()
@@ -46,6 +55,29 @@ pr = cProfile.Profile(); pr.enable()
 for k in range(5):
     fd = tr.get_data([nf]); tr.last_is_keyframe = False; tr.add_data(fd)
     for _ in range(10):
-        losses, _ = tr.step(sync=False); float(losses["total_loss"])
+        losses, _ = tr.step(); float(losses["total_loss"])
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+
+# ---- inside get_data (fast mode), line by line ------------------------------------------------------------
+import numpy as np
+from isdf_b200.datasets.data_util import FrameData
+acc = {}
+def tick(name, t0):
+    torch.cuda.synchronize(); t1 = time.perf_counter(); acc[name] = acc.get(name, 0.0) + (t1 - t0); return t1
+for k in range(10):
+    tr.scene_dataset[200 + k]
+for k in range(10):
+    for _ in range(3):
+        tr.step()
+    t = time.perf_counter()
+    s = tr.scene_dataset[200 + k]; t = tick("dataset[]", t)
+    im_np, depth_np, T_np = s["image"][None, ...], s["depth"][None, ...], s["T"][None, ...]
+    tr._stage_evt.synchronize(); t = tick("stage_evt.sync", t)
+    np.copyto(tr._stage[0].numpy(), depth_np, casting="same_kind"); np.copyto(tr._stage[1].numpy(), T_np, casting="same_kind"); t = tick("copyto pinned", t)
+    depth = tr._stage[0].to(tr.device, non_blocking=True); T = tr._stage[1].to(tr.device, non_blocking=True); tr._stage_evt.record(); t = tick("h2d", t)
+    data = FrameData(frame_id=np.array([200 + k]), im_batch=None, im_batch_np=im_np, depth_batch=depth, depth_batch_np=depth_np, T_WC_batch=T, T_WC_batch_np=T_np); t = tick("FrameData()", t)
+    data.normal_batch = tr.sdf_map.engine().ingest_normals(depth[0], tr.cam)[None, :]; t = tick("normals", t)
+    out = FrameData(); out.add_frame_data(data, replace=False); t = tick("out.add", t)
+    tr.last_is_keyframe = False; tr.add_data(out); t = tick("tr.add_data", t)
+print("get_data pieces, ms per ingest (each followed by a device sync):", {k: round(1e2 * v, 3) for k, v in acc.items()})

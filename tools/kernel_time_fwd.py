@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from oracle import isdf_oracle as O
 from tests.golden import common as C
 from tests import parity as P

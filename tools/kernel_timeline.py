@@ -1,6 +1,6 @@
 import os, sys, torch
 os.environ["ISDFB_DEBUG_CLOCK"]="1"
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from oracle import isdf_oracle as O
 from tests.golden import common as C
 from tests import parity as P

@@ -1,0 +1,86 @@
+"""N-GPU check of the fused gradient exchange (C1 fused into K4) against the NCCL all-reduce.
+   torchrun --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/test_exchange_2gpu.py"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+dev = torch.device("cuda", lr)
+torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+import __graft_entry__ as ge
+if rank == 0:
+    ge.build()
+dist.barrier()
+from oracle import isdf_oracle as O
+from tests.golden import common as C
+from tests import parity as P
+from isdf_b200 import parallel
+import bench
+
+def say(*a):
+    if rank == 0:
+        print(*a, flush=True)
+
+# ---- engine level: multimem flush == NCCL sum ---------------------------------------------------------------
+cfg = O.default_cfg(noise_std=0.05)
+sd = C.golden_weights(17, gain=1.5)
+batch, noise = C.loss_batch(100 + rank, 300)            # every rank its own rays
+eng = P.make_engine(dev, cfg, "bf16x3", max_points=32768)
+eng.pack_weights(P.flat_params(sd, dev))
+b = {k: v.to(dev) for k, v in batch.items()}
+lc = P.loss_cfg_from(cfg, 300 * 27)
+nz = noise.to(dev)
+def k4():
+    eng.train_fwd_bwd(b["pc"], b["z_vals"], b["depth_sample"], b["dirs_C_sample"], b["T_WC_sample"], b["norm_sample"], nz, lc)
+eng.zero_grad(); k4()
+ref = eng.grad_buffer().clone()
+dist.all_reduce(ref)
+ex, err = parallel.try_grad_exchange(eng, dev)
+say("exchange:", "multicast OK" if ex else "UNAVAILABLE %r" % (err,))
+if ex is not None:
+    for par in (0, 1, 0):
+        eng.select_grad_buffer(par)
+        k4()
+        eng.zero_grad_buffer(1 - par)
+        ex.barrier()
+        got = eng.grad_buffer().clone()
+        e = float((got - ref).abs().max() / ref.abs().max())
+        say("parity %d: max |fused - nccl| / max|nccl| = %.3g" % (par, e))
+        assert e < 1e-5, e
+        torch.cuda.synchronize(); dist.barrier()
+    ex.close()
+del eng
+
+# ---- trainer level: same trajectory, timing ------------------------------------------------------------------------
+from isdf.modules import trainer as trainer_mod
+res = {}
+for mode in ("nccl", "auto"):
+    np.random.seed(1 + rank); torch.manual_seed(1 + rank)
+    wl = bench.WORKLOADS["default"]
+    c = bench.make_config(wl, "bf16x3", "fast")
+    c["b200"]["grad_exchange"] = mode
+    tr = trainer_mod.Trainer(dev, c, incremental=True)
+    dist.broadcast(tr.sdf_map.flat_parameters(), 0)
+    for i in range(wl["keyframes"]):
+        tr.last_is_keyframe = True
+        tr.add_data(tr.get_data([rank + i * world]))
+    for _ in range(10):
+        tr.step(sync=False)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        tr.step(sync=False)
+    torch.cuda.synchronize(); dist.barrier()
+    ms = 1e3 * (time.perf_counter() - t0) / 200
+    flat = tr.sdf_map.flat_parameters().clone()
+    chk = flat.clone(); dist.broadcast(chk, 0)
+    res[mode] = (ms, flat, float((flat - chk).abs().max()))
+    say("mode %-5s exchange=%s nccl_in_graph=%s: %.3f ms/step; replicas differ by %.3g" %
+        (mode, "multicast" if tr._xchg is not None else "nccl", tr._nccl_in_graph, ms, res[mode][2]))
+    del tr
+say("params after 210 steps, |auto - nccl| max = %.3g (of max %.3g)" %
+    (float((res["auto"][1] - res["nccl"][1]).abs().max()), float(res["nccl"][1].abs().max())))
+dist.destroy_process_group()
