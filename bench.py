@@ -328,7 +328,10 @@ def main():
                "config": {"workload": wl["name"], "rays_per_step_per_gpu": rays_per_step, "samples_per_ray": S,
                           "points_per_step_per_gpu": pts_per_step, "keyframes_per_gpu": wl["keyframes"],
                           "precision": args.precision, "rng_mode": "fast (fixed shapes, validity mask, no host sync; whole step replayed as one CUDA graph)",
-                          "parallelism": "dp%d (keyframe-sharded, one NCCL all-reduce of the packed gradient)" % world,
+                          "parallelism": "dp%d (keyframe-sharded; gradient exchange: %s)" % (world, (
+                              "none" if world == 1 else
+                              "fused into the weight-gradient kernel over NVLink multicast (multimem.red) + 1 barrier" if tr._xchg is not None
+                              else "one NCCL all-reduce of the packed gradient%s" % (" inside the step graph" if tr._nccl_in_graph else ""))),
                           "l2": "no explicit flush: keyframe buffer %.0f MB and per-step side state %.0f MB both exceed the 126 MB L2"
                                 % (wl["keyframes"] * wl["H"] * wl["W"] * 16 / 1e6, pts_per_step * 0.041)},
                "clocks": clocks,

@@ -199,9 +199,11 @@ int isdfb_grad_buffer(isdfb_ctx* ctx, float** ptr, int64_t* n_floats);
  * Data-parallel ranks (one process per GPU, keyframes sharded -- SURVEY.md 8e) exchange ONE thing per
  * step: the packed parameter gradient.  Instead of a separate all-reduce, the caller allocates two
  * gradient buffers in symmetric memory (same virtual layout on every rank, plus an NVLink-multicast
- * alias of each) and installs them here; K4 then flushes its gradient tiles with `multimem.red` into the
- * multicast alias, so every rank's copy receives the sum over ranks inside the NVSwitch while the
- * kernel is still draining.  Protocol per step n (b = n mod 2), driven by the caller on one stream:
+ * alias of each) and installs them here.  K4's weight-gradient kernel then accumulates its split-K
+ * partial tiles in a local stage, and the LAST CTA of every 128 x 256 gradient tile forwards the finished
+ * tile with `multimem.red` into the multicast alias: every rank's copy receives the sum over ranks
+ * inside the NVSwitch, tile by tile while the kernel is still draining, and exactly the gradient's size
+ * (2 MB) crosses the fabric per rank and step.  Protocol per step n (b = n mod 2), driven by the caller on one stream:
  *     isdfb_select_grad_buffer(b); K4 (accumulates into buffer b on ALL ranks);
  *     isdfb_zero_grad_buffer(1-b)  (own copy, for step n+1);  cross-rank barrier;  K6 (reads own copy b).
  * Buffer 1-b is zeroed BEFORE the barrier, so no rank can add into it for step n+1 before its owner

@@ -259,6 +259,11 @@ int isdfb_set_grad_exchange(isdfb_ctx* ctx, float* local0, float* local1, float*
   if (ctx->cfg.precision == ISDFB_PREC_FP32)
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_set_grad_exchange: the fused exchange is implemented by the tensor-core path's "
                                    "gradient flush; fp32 mode uses the caller's all-reduce on isdfb_grad_buffer");
+  {   // the library's own buffer becomes the local STAGE of the weight-gradient kernel: start it clean (setup call, may sync)
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaMemset(ctx->g_own, 0, ctx->lay.n_packed * sizeof(float));
+    if (e != cudaSuccess) ISDFB_FAIL(ctx, ISDFB_ERR_CUDA, "isdfb_set_grad_exchange: %s", cudaGetErrorString(e));
+  }
   ctx->g_local[0] = local0; ctx->g_local[1] = local1;
   ctx->g_mc[0] = mcast0; ctx->g_mc[1] = mcast1;
   ctx->g_sel = 0;

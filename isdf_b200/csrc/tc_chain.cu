@@ -11,7 +11,10 @@
 //               columns of every K chunk of the next step's A operand; 4 warps per scheduler hide the
 //               ALU/SFU/LSU latency of the element-wise math; chunk 0 of the next A operand is done
 //               after a quarter of the epilogue, so the next MMA runs under the rest of it;
-//   warp 16     MMA issuer (+ TMEM alloc);      warp 17   weight producer (+ L2 prefetch of side arrays).
+//   warp 16     MMA issuer (+ TMEM alloc);      warp 17   weight producer (+ L2 prefetch of side arrays);
+//   warps 18-19 idle: they complete the helper WARPGROUP, which hands registers back (setmaxnreg.dec 32) so
+//               that the four epilogue warpgroups can grow from the launch-time 96 to 112 registers per thread
+//               (the launch bound is 65536 / 640 threads) -- room for operand prefetch two sub-pieces ahead.
 //
 // Precision: kPasses = 3 -> every product is A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with bf16 hi/lo splits
 // and fp32 accumulation (~fp32 accuracy); kPasses = 1 -> single bf16 pass (fast mode).
@@ -20,7 +23,9 @@
 
 #define EPI_WARPS 16
 #define EPI_THREADS (EPI_WARPS * 32)
-#define NUM_THREADS (EPI_THREADS + 64)
+#define NUM_THREADS (EPI_THREADS + 128)   // + one helper warpgroup: MMA issuer, weight producer, two idle warps
+#define EPI_REGS 112                     // setmaxnreg moves registers inside the CTA's launch-time pool (640 x 96):
+#define HELPER_REGS 32                   // 512 x 112 + 128 x 32 = 61 440 = 640 x 96 exactly
 #define K_STEP 16                        // K elements per weight-ring stage (one UMMA K step)
 #define N_KSTEPS (TC_H / K_STEP)         // 16
 #define A_IMG_BYTES (TC_TILE * TC_H * 2) // 64 KB
@@ -42,6 +47,13 @@ struct ChainSmemTail {       // lives after the operand buffers and the scratch
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// 16-byte load of per-tile side state: read once, never re-used by this SM -> do not allocate in the (tiny:
+// 228 KB - 216 KB of shared memory) L1, whose lines would otherwise all be tied up by in-flight fills
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 v;
+  asm("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
@@ -70,7 +82,7 @@ struct EpiStepPtrs {                  // per-step pointers (thread offsets inclu
   const float *bias, *wout;
   float* hlast;
   const float* e32;                   // this thread's slice of the fp32 embedding side array (same offsets as aux)
-  int ablate;
+  int ablate, stream;
 };
 __device__ __forceinline__ uint32_t sub_a(int c, int h) { return (uint32_t)(8 * c + h) * A_LBO; }
 __device__ __forceinline__ uint32_t sub_d(int c, int h) { return (uint32_t)(8 * c + h) * 256u; }
@@ -94,20 +106,21 @@ __device__ __forceinline__ void put8(const EpiT& T, const float* x, int c, int h
 template <int EPI, int kPasses>
 __device__ __forceinline__ void epi_load(const EpiStepPtrs& P, bool l_is_cat, int c, int h, EpiOps& o) {
   if (P.ablate & 8) return;
+  auto ld = [&](const void* q) -> uint4 { return P.stream ? ld_stream(q) : *reinterpret_cast<const uint4*>(q); };
   if (EPI == EPI_S2 || EPI == EPI_S3 || EPI == EPI_S3_LAST || EPI == EPI_S4)
-    o.s = *reinterpret_cast<const uint4*>(P.sigp + sub_a(c, h));
+    o.s = ld(P.sigp + sub_a(c, h));
   if (EPI == EPI_S3 || EPI == EPI_S3_LAST) {
-    o.b0 = *reinterpret_cast<const uint4*>(P.dhi + sub_d(c, h));
-    if (kPasses == 3) o.b1 = *reinterpret_cast<const uint4*>(P.dlo + sub_d(c, h));
+    o.b0 = ld(P.dhi + sub_d(c, h));
+    if (kPasses == 3) o.b1 = ld(P.dlo + sub_d(c, h));
   } else if (EPI == EPI_S4) {
-    o.b0 = *reinterpret_cast<const uint4*>(P.zb2 + sub_x(c, h));
-    o.b1 = *reinterpret_cast<const uint4*>(P.zb2 + sub_x(c, h) + 512);
+    o.b0 = ld(P.zb2 + sub_x(c, h));
+    o.b1 = ld(P.zb2 + sub_x(c, h) + 512);
   } else if (EPI == EPI_S2_END || ((EPI == EPI_S1 || EPI == EPI_S1_LAST) && l_is_cat)) {
-    o.b0 = *reinterpret_cast<const uint4*>(P.part_in + sub_x(c, h));
-    o.b1 = *reinterpret_cast<const uint4*>(P.part_in + sub_x(c, h) + 512);
+    o.b0 = ld(P.part_in + sub_x(c, h));
+    o.b1 = ld(P.part_in + sub_x(c, h) + 512);
     if (EPI == EPI_S2_END) {
-      o.e0 = *reinterpret_cast<const uint4*>(P.e32 + sub_x(c, h));
-      o.e1 = *reinterpret_cast<const uint4*>(P.e32 + sub_x(c, h) + 512);
+      o.e0 = ld(P.e32 + sub_x(c, h));
+      o.e1 = ld(P.e32 + sub_x(c, h) + 512);
     }
   }
 }
@@ -270,27 +283,28 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
     }
   }
   if (kWide) {
-    // both 8-column halves of a chunk in one straight-line block: one 16-column TMEM load, then two independent
-    // dependency chains the scheduler can interleave; the side operands of the next chunk are requested as
-    // soon as this chunk's are in registers (a whole chunk ahead)
+    // operands of BOTH sub-pieces of the next chunk are requested before this chunk is processed: two sub-pieces
+    // of lead on the side-state loads (L2 latency under load exceeds one) at the price of two more operand sets
     epi_load<EPI, kPasses>(P, l_is_cat, T.c0, 1, ob);
 #pragma unroll 1
     for (int ci = 0; ci < 4; ++ci) {
       const int c = (ci + T.c0) & 3;
-      float v[16];
-      tmem_ld16(d_tmem + 64 * c + T.kcol, v);
-      const EpiOps ca = oa, cb = ob;
+      EpiOps na = oa, nb = ob;
       if (ci < 3) {
-        epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 0, oa);
-        epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 1, ob);
+        epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 0, na);
+        epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 1, nb);
       }
-      epi_sub<EPI, kPasses>(args, T, P, ca, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
-      epi_sub<EPI, kPasses>(args, T, P, cb, v + 8, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      float v[8];
+      tmem_ld8(d_tmem + 64 * c + T.kcol, v);
+      epi_sub<EPI, kPasses>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      tmem_ld8(d_tmem + 64 * c + T.kcol + 8, v);
+      epi_sub<EPI, kPasses>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
       if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
       }
+      oa = na; ob = nb;
     }
   } else {
 #pragma unroll 1
@@ -349,7 +363,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
   const int rot = args.stagger ? (int)(blockIdx.x & 15u) : 0;
   const int my_tiles = (args.n_tiles > (int)blockIdx.x) ? (args.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp == EPI_WARPS + 1) {
+  // (setmaxnreg sits INSIDE each role branch: ptxas budgets registers per branch only when the re-allocation
+  // dominates the branch; placed before the dispatch it constrains the whole kernel to the smallest value)
+  if (warp >= EPI_WARPS + 2) {
+    reg_dec<HELPER_REGS>();          // idle warps of the helper warpgroup
+  } else if (warp == EPI_WARPS + 1) {
+    reg_dec<HELPER_REGS>();
     // ===================== weight producer =====================
     if (elect_one()) {
       uint32_t j = 0;
@@ -398,6 +417,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
       }
     }
   } else if (warp == EPI_WARPS) {
+    reg_dec<HELPER_REGS>();
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
     uint32_t j = 0, n = 0;
@@ -429,6 +449,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
       }
     }
   } else {
+    reg_inc<EPI_REGS>();
     // ===================== epilogue: thread = (point, 4 x 16 columns) =====================
     // Warp (q, jg) owns points 32q..32q+31 and, inside every 64-column K chunk c of the next A operand,
     // columns [64c+16jg, 64c+16jg+16): chunk 0 is complete after a quarter of the epilogue, so the MMA
@@ -527,6 +548,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         P.hlast = T.aux + (size_t)args.arr_hlast * T.aux_stride;
         P.e32 = e32_w;
         P.ablate = args.ablate;
+        P.stream = args.stream_loads;
         EpiAcc acc = {0.f, 0.f, 0.f, 0.f};
         if (dbg) args.dbg_clock[1 + 2 * s] = clock64();
         switch (epi) {

@@ -178,6 +178,10 @@ __device__ __forceinline__ void unpack_unorm16x8(const uint4& v, float* s) {
     s[2 * i + 1] = fminf(b * c, 1.f);
   }
 }
+// warp-specialised register re-allocation (whole warpgroups = 4 consecutive warps): the helper warpgroup gives
+// registers back, the epilogue warpgroups take them
+template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -141,21 +141,72 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const TcDwArgs arg
         tmem_ld32(tmem + lane_addr + c * 32, v);
         if (job.perm_half > 0) {     // embedding-fed unit: internal column order -> the reference's (pe_nat_col)
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            grad_add(grow + pe_nat_col(c * 32 + i, job.perm_half), v[i], args.g_mc);
+          for (int i = 0; i < 32; ++i) grad_add(grow + pe_nat_col(c * 32 + i, job.perm_half), v[i], 0);
           continue;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          grad_add4(grow + c * 32 + i * 4, v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3], args.g_mc);
+        for (int i = 0; i < 8; ++i) grad_add4(grow + c * 32 + i * 4, v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3], 0);
       }
     }
     if (has_db || has_dw) {
       tmem_ld32(tmem + lane_addr + 256, v);
-      if (has_db) grad_add(args.g_packed + job.db_off + row, v[0], args.g_mc);
-      if (has_dw) grad_add(args.g_packed + args.wout_off + row, args.scale_output * v[16], args.g_mc);
+      if (has_db) grad_add(args.g_packed + job.db_off + row, v[0], 0);
+      if (has_dw) grad_add(args.g_packed + args.wout_off + row, args.scale_output * v[16], 0);
     }
     tc_fence_before();
+  }
+  if (args.g_mc && warp >= 2) {
+    // C1 fused: the LAST CTA of a job (over all launches of the step) forwards the job's finished 128 x 256 tile
+    // from the local staging buffer to every rank's gradient through the NVLink-multicast alias (multimem.red)
+    // and clears the stage for the next step: 2 MB per rank per step cross the fabric, tile by tile as jobs finish.
+    __shared__ int s_last;
+    __threadfence();
+    named_bar_sync(2, 128);
+    if (threadIdx.x == 64) {
+      const int prev = (my_tiles > 0) ? atomicAdd(args.counters + job_id, 1) : -1;
+      s_last = (prev == args.expect[job_id] - 1) ? 1 : 0;
+      if (s_last) args.counters[job_id] = 0;
+    }
+    named_bar_sync(2, 128);
+    if (s_last) {
+      __threadfence();
+      const int q = warp & 3;
+      const int row = job.half * 128 + q * 32 + lane;
+      bool has_main = false, has_db = false, has_dw = false;
+      for (int pi = 0; pi < job.n_pairs; ++pi) {
+        has_main |= job.pair[pi].y_arr >= 0;
+        has_db |= job.pair[pi].ones == 1;
+        has_dw |= job.pair[pi].ones == 2;
+      }
+      if (has_main) {
+        // the tile's 128 rows x 256 floats, 2 KB (two rows) per pass of the 128 flush threads, 8 loads in flight
+        const int t = threadIdx.x - 64;                 // 0..127
+        const size_t base = job.g_off + (size_t)(job.half * 128) * job.ld;
+        float4* src = reinterpret_cast<float4*>(args.g_packed + base) + t;
+        float* dst = args.g_mc_out + base + (size_t)t * 4;
+#pragma unroll 1
+        for (int it = 0; it < 64; it += 8) {
+          float4 r[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) r[u] = __ldcg(src + (size_t)(it + u) * 128);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            grad_add4(dst + (size_t)(it + u) * 512, r[u].x, r[u].y, r[u].z, r[u].w, 1);
+            __stcg(src + (size_t)(it + u) * 128, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        }
+      }
+      if (has_db) {
+        float* p = args.g_packed + job.db_off + row;
+        grad_add(args.g_mc_out + job.db_off + row, __ldcg(p), 1);
+        __stcg(p, 0.f);
+      }
+      if (has_dw) {
+        float* p = args.g_packed + args.wout_off + row;
+        grad_add(args.g_mc_out + args.wout_off + row, __ldcg(p), 1);
+        __stcg(p, 0.f);
+      }
+    }
   }
 
   tc_fence_before();

@@ -33,6 +33,7 @@ void tc_destroy(isdfb_ctx* ctx) {
   if (tc->dwl_hi) cudaFree(tc->dwl_hi);
   if (tc->dwl_lo) cudaFree(tc->dwl_lo);
   if (tc->sig16) cudaFree(tc->sig16);
+  if (tc->dw_counters) cudaFree(tc->dw_counters);
   if (tc->side) cudaStreamDestroy(tc->side);
   if (tc->ev_fork) cudaEventDestroy(tc->ev_fork);
   if (tc->ev_join) cudaEventDestroy(tc->ev_join);
@@ -82,6 +83,8 @@ int tc_create(isdfb_ctx* ctx) {
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->sig16, tc->dwl_stride * L));
   if (ctx->cfg.precision == ISDFB_PREC_BF16X3) ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dwl_lo, tc->dwl_stride * tc->n_dwl));
 
+  ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dw_counters, TC_MAX_JOBS * sizeof(int32_t)));
+  ISDFB_CUDA_OK(ctx, cudaMemset(tc->dw_counters, 0, TC_MAX_JOBS * sizeof(int32_t)));
   if (getenv("ISDFB_DEBUG_CLOCK")) {
     ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dbg_clock, 128 * sizeof(long long)));
     ISDFB_CUDA_OK(ctx, cudaMemset(tc->dbg_clock, 0, 128 * sizeof(long long)));
@@ -93,7 +96,8 @@ int tc_create(isdfb_ctx* ctx) {
     a.mode = mode; a.L = L; a.ic = ic; a.E = lay.E;
     a.prefetch = getenv("ISDFB_NO_PREFETCH") ? 0 : 1;
     a.stagger = getenv("ISDFB_STAGGER") ? atoi(getenv("ISDFB_STAGGER")) : 1;
-    a.wide = getenv("ISDFB_EPI_WIDE") ? atoi(getenv("ISDFB_EPI_WIDE")) : 0;
+    a.stream_loads = getenv("ISDFB_STREAM_LOADS") ? atoi(getenv("ISDFB_STREAM_LOADS")) : 1;
+    a.wide = getenv("ISDFB_EPI_WIDE") ? atoi(getenv("ISDFB_EPI_WIDE")) : 1;
     a.ablate = getenv("ISDFB_ABLATE") ? atoi(getenv("ISDFB_ABLATE")) : 0;
     a.dbg_clock = tc->dbg_clock;
     a.pe = ctx->pe;
@@ -193,6 +197,29 @@ int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* 
              float* loss_sums, cudaStream_t st) {
   TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
   const int64_t n = n_rays * S;
+  const bool two_wave_ok = !tc->profiling && !getenv("ISDFB_NO_OVERLAP");
+  // weight-gradient launches of this step as (grid, tiles): with a gradient exchange installed the last CTA of
+  // each job over ALL of them forwards the job's tile to the multicast buffer, so it must know how many arrive
+  int32_t expect[TC_MAX_JOBS] = {0};
+  if (ctx->g_xchg) {
+    auto plan = [&](int grid, int tiles) {
+      for (int j = 0; j < tc->dw.n_jobs; ++j) {
+        const int n_splits = (grid - 1 - j) / tc->dw.n_jobs + 1;
+        expect[j] += n_splits < tiles ? n_splits : tiles;
+      }
+    };
+    for (int64_t p0 = 0; p0 < n; p0 += ctx->cap) {
+      const int64_t nc = (n - p0 < ctx->cap) ? (n - p0) : ctx->cap;
+      const int tiles = (int)((nc + TC_TILE - 1) / TC_TILE);
+      if (tiles > tc->num_sms && tiles < 2 * tc->num_sms && two_wave_ok) {
+        const int rest = tiles - tc->num_sms;
+        plan(tc->num_sms - rest > 14 ? tc->num_sms - rest : 14, tc->num_sms);
+        plan(tc->num_sms, rest);
+      } else {
+        plan(tc->num_sms, tiles);
+      }
+    }
+  }
   for (int64_t p0 = 0; p0 < n; p0 += ctx->cap) {
     const int64_t nc = (n - p0 < ctx->cap) ? (n - p0) : ctx->cap;
     TcChainArgs a = tc->proto[TC_MODE_TRAIN];
@@ -215,10 +242,13 @@ int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* 
     const int total_tiles = a.n_tiles;
     const int pi = prof_begin(tc, st);
     TcDwArgs d = tc->dw;
-    d.g_packed = a.g_packed;
-    d.g_mc = a.g_mc;
+    d.g_mc = ctx->g_xchg ? 1 : 0;
+    d.g_packed = ctx->g_xchg ? ctx->g_own : ctx->g_packed;      // exchange: accumulate in the local stage ...
+    d.g_mc_out = ctx->g_xchg ? ctx->g_mc[ctx->g_sel] : nullptr; // ... the last CTA per job forwards it
+    d.counters = tc->dw_counters;
+    for (int j = 0; j < TC_MAX_JOBS; ++j) d.expect[j] = expect[j];
     int rc;
-    if (total_tiles > tc->num_sms && total_tiles < 2 * tc->num_sms && !tc->profiling && !getenv("ISDFB_NO_OVERLAP")) {
+    if (total_tiles > tc->num_sms && total_tiles < 2 * tc->num_sms && two_wave_ok) {
       // two waves: the weight gradients of wave 1 run on a side stream underneath the (partial) wave 2
       a.tile0 = 0; a.n_tiles = tc->num_sms;
       rc = tc_chain_launch(ctx, a, passes_of(ctx), tc->num_sms, st);

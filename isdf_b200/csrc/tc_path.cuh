@@ -24,8 +24,12 @@ struct TcDwArgs {
   int32_t skip_ylo;        // experiment: drop the X_hi*Y_lo pass (Y = layer inputs rounded to bf16)
   const uint8_t *dwl_hi, *dwl_lo;
   size_t dwl_stride;
-  float* g_packed;
-  int32_t g_mc;            // 1: g_packed is a multicast address
+  float* g_packed;         // where the TMEM accumulators are flushed (red.global.add): the gradient itself, or with an
+                           // exchange installed the LOCAL staging buffer
+  int32_t g_mc;            // 1: exchange installed -- the last CTA of every job forwards the job's finished tile
+  float* g_mc_out;         //    from the staging buffer to this MULTICAST address (multimem.red) and clears the stage
+  int32_t* counters;       //    per-job arrival counters (self-resetting)
+  int32_t expect[TC_MAX_JOBS];   // arrivals per job over ALL weight-gradient launches of the step
   int64_t wout_off;
   float scale_output;
 };
@@ -46,6 +50,7 @@ struct TcState {
   cudaEvent_t ev[TC_PROF_MAX][3];   // before chain, after chain, after dW
   int ev_kind[TC_PROF_MAX];         // 1: chain only, 2: chain + dW
   int n_ev;
+  int32_t* dw_counters;    // device, [TC_MAX_JOBS], zero between steps
   cudaStream_t side;       // second stream: weight gradients of the first wave overlap the second wave
   cudaEvent_t ev_fork, ev_join;
   long long* dbg_clock;    // device buffer [128] when ISDFB_DEBUG_CLOCK is set

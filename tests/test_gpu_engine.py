@@ -322,6 +322,20 @@ def test_errors_are_loud():
         eng.pack_weights(torch.zeros(10, device=DEV))
     with pytest.raises(RuntimeError):
         P.make_engine(torch.device("cpu"), O.default_cfg())
+    # 'pc' bound: the two precomputed arrays go together (host check and C-ABI check)
+    with pytest.raises(ValueError):
+        P.loss_cfg_from(O.default_cfg(), 10, bounds=torch.zeros(2, 5, device=DEV))
+    # gradient exchange: refused for the CUDA-core mode, and buffer selection needs an installed exchange
+    buf = torch.zeros(4, device=DEV)
+    with pytest.raises(_lib.IsdfbError):
+        eng.set_grad_exchange(buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), 4)
+    with pytest.raises(_lib.IsdfbError):
+        eng.select_grad_buffer(0)
+    tc = _engine(O.default_cfg(), "bf16x3", max_points=1024)
+    with pytest.raises(_lib.IsdfbError):                         # buffers smaller than the packed gradient
+        tc.set_grad_exchange(buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), 4)
+    with pytest.raises(_lib.IsdfbError):
+        tc.zero_grad_buffer(1)
 
 
 # ---------------------------------------------------------------------------------- N3

@@ -54,33 +54,53 @@ if ex is not None:
     ex.close()
 del eng
 
-# ---- trainer level: same trajectory, timing ------------------------------------------------------------------------
+# ---- trainer level: same trajectory (eager: identical RNG consumption), then timing with graphs -------------------
 from isdf.modules import trainer as trainer_mod
-res = {}
-for mode in ("nccl", "auto"):
+import torch.distributed._symmetric_memory as symm_mem
+t = symm_mem.empty(1024, dtype=torch.float32, device=dev)
+h = symm_mem.rendezvous(t, dist.group.WORLD)
+for _ in range(10):
+    h.barrier(channel=0)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(200):
+    h.barrier(channel=0)
+torch.cuda.synchronize()
+say("symmetric-memory barrier: %.1f us each (200 back to back)" % (1e6 * (time.perf_counter() - t0) / 200))
+
+def run(mode, graph, steps):
     np.random.seed(1 + rank); torch.manual_seed(1 + rank)
     wl = bench.WORKLOADS["default"]
     c = bench.make_config(wl, "bf16x3", "fast")
     c["b200"]["grad_exchange"] = mode
+    c["b200"]["cuda_graph"] = graph
     tr = trainer_mod.Trainer(dev, c, incremental=True)
     dist.broadcast(tr.sdf_map.flat_parameters(), 0)
-    for i in range(wl["keyframes"]):
-        tr.last_is_keyframe = True
-        tr.add_data(tr.get_data([rank + i * world]))
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        for i in range(wl["keyframes"]):
+            tr.last_is_keyframe = True
+            tr.add_data(tr.get_data([rank + i * world]))
     for _ in range(10):
         tr.step(sync=False)
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(200):
+    for _ in range(steps):
         tr.step(sync=False)
     torch.cuda.synchronize(); dist.barrier()
-    ms = 1e3 * (time.perf_counter() - t0) / 200
+    ms = 1e3 * (time.perf_counter() - t0) / steps
     flat = tr.sdf_map.flat_parameters().clone()
     chk = flat.clone(); dist.broadcast(chk, 0)
-    res[mode] = (ms, flat, float((flat - chk).abs().max()))
-    say("mode %-5s exchange=%s nccl_in_graph=%s: %.3f ms/step; replicas differ by %.3g" %
-        (mode, "multicast" if tr._xchg is not None else "nccl", tr._nccl_in_graph, ms, res[mode][2]))
-    del tr
-say("params after 210 steps, |auto - nccl| max = %.3g (of max %.3g)" %
-    (float((res["auto"][1] - res["nccl"][1]).abs().max()), float(res["nccl"][1].abs().max())))
+    kind = "multicast" if tr._xchg is not None else "nccl"
+    say("mode %-9s graph=%d -> exchange=%s nccl_in_graph=%s: %.3f ms/step; replicas differ by %.3g" %
+        (mode, graph, kind, tr._nccl_in_graph, ms, float((flat - chk).abs().max())))
+    if tr._xchg is not None:
+        tr._xchg.close()
+    return flat
+
+a = run("nccl", 0, 40)
+b = run("multicast", 0, 40)
+say("eager, same RNG: params after 50 steps |multicast - nccl| max = %.3g (of max %.3g)" %
+    (float((a - b).abs().max()), float(a.abs().max())))
+run("nccl", 1, 300)
+run("multicast", 1, 300)
 dist.destroy_process_group()
