@@ -175,7 +175,7 @@ def test_train_properties_full_size(mode):
     b = P.run_train(_engine(cfg, mode, max_points=4096), sd, batch, noise, cfg, DEV)
     # tensor-core modes: a tile's K order is rotated per CTA (tc_chain.cu rot_kstep), so a point that lands on
     # another CTA after re-chunking sees a different fp32 summation order -> equal up to rounding, not bit-wise
-    assert P.rel(a["sdf"], b["sdf"]) < (1e-6 if mode == "fp32" else 2e-5)
+    assert P.rel(a["sdf"], b["sdf"]) < {"fp32": 1e-6, "bf16x3": 5e-5, "bf16": 2e-2}[mode]
     assert max(P.rel_fro(x, y) for x, y in zip(a["grads"], b["grads"])) < max(1e-4, 0.1 * t["gw"])
     assert abs(float(a["loss_mat"].double().mean()) - float(a["sums"][3]) / (R * 27)) < 1e-5
     # additivity: grads(first half) + grads(second half) == grads(all) at fixed inv_count

@@ -19,6 +19,9 @@ DEV = torch.device("cuda:0")
 MODES = [m for m in os.environ.get("ISDFB_TEST_MODES", "fp32,bf16x3,bf16").split(",") if m]
 TOL_SDF = {"fp32": 5e-6, "bf16x3": 1e-4, "bf16": 5e-2}
 TOL_G = {"fp32": 1e-4, "bf16x3": 1e-3, "bf16": 0.5}
+# the same point evaluated by another CTA (other chunking): tensor-core modes rotate the K order per CTA
+# (tc_chain.cu rot_kstep), so results agree up to fp32 summation order, not bit-wise
+TOL_RECHUNK = {"fp32": 1e-6, "bf16x3": 5e-5, "bf16": 2e-2}
 
 
 def load(name):
@@ -55,7 +58,7 @@ def test_grid_sdf_matches_reference_chunks(mode):
         a = fc_map.chunks(pc, 500, m)                                       # the reference's call pattern
         b = m(pc)                                                           # one call, chunked inside the library
     assert P.rel(a.cpu().view(12, 12, 12), g["sdf"]) < TOL_SDF[mode]
-    assert torch.equal(a, b)
+    assert P.rel(a.cpu(), b.cpu()) < TOL_RECHUNK[mode]
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -73,7 +76,7 @@ def test_grid_200_cubed_properties(mode):
     m2 = _map(75, 1.0, None, mode, max_points=4096)
     with torch.no_grad():
         sdf2 = m2(pc[sub].contiguous())
-    assert P.rel(sdf[sub].cpu(), sdf2.cpu()) < 1e-6
+    assert P.rel(sdf[sub].cpu(), sdf2.cpu()) < TOL_RECHUNK[mode]
     layers = [(w.double(), b.double()) for w, b in O.layers_from_state_dict(C.golden_weights(75), 2)]
     ref = O.sdf_forward(layers, pc[sub].cpu().double(), cfg)
     assert P.rel(sdf[sub].cpu(), ref) < TOL_SDF[mode]
