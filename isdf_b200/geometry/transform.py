@@ -4,6 +4,7 @@ pointcloud_from_depth_torch 169-196, estimate_pointcloud_normals 215-270).
 
 The training kernels recompute ray directions from pixel indices; these torch versions serve the
 callers around the step (frame ingest, visualisation) and are not used inside Trainer.step()."""
+import numpy as np
 import torch
 
 
@@ -23,6 +24,40 @@ def origin_dirs_W(T_WC, dirs_C):
     """World-frame ray origins and directions: t_WC and R_WC d_C."""
     dirs_W = (T_WC[:, :3, :3] * dirs_C[..., None, :]).sum(dim=-1)
     return T_WC[:, :3, -1], dirs_W
+
+
+def normalize(x):
+    """Unit vector of a 1-D numpy array (transform.py:44-46)."""
+    assert x.ndim == 1, "x must be a vector (ndim: 1)"
+    return x / np.linalg.norm(x)
+
+
+def pointcloud_from_depth(depth, fx, fy, cx, cy, depth_type="z", skip=1):
+    """numpy back-projection of a float depth image [H,W] -> [H/skip,W/skip,3]; NaN stays NaN (transform.py:141-166)."""
+    assert depth_type in ["z", "euclidean"], "Unexpected depth_type"
+    assert depth.dtype.kind == "f", "depth must be float and have meter values"
+    rows, cols = depth.shape
+    c = np.arange(cols, step=skip)[None, :]
+    r = np.arange(rows, step=skip)[:, None]
+    z = depth[::skip, ::skip]
+    bad = np.isnan(z)
+    x = np.where(bad, np.nan, z * (c - cx) / fx)
+    y = np.where(bad, np.nan, z * (r - cy) / fy)
+    pc = np.dstack((x, y, z))
+    if depth_type == "euclidean":
+        pc = pc * (z / np.linalg.norm(pc, axis=2))[:, :, None]
+    return pc
+
+
+def backproject_pointclouds(depths, fx, fy, cx, cy):
+    """[B,H,W] depth images -> [B,H*W,3] camera-frame points (transform.py:127-138)."""
+    return np.stack([pointcloud_from_depth(d, fx, fy, cx, cy).reshape(-1, 3) for d in depths], axis=0)
+
+
+def pc_bounds(pc):
+    """Axis-aligned extents and centre of an [N,3] point array (transform.py:199-212)."""
+    lo, hi = pc[:, :3].min(axis=0), pc[:, :3].max(axis=0)
+    return hi - lo, (hi + lo) / 2.0
 
 
 def transform_3D_grid(grid_3d, transform=None, scale=None):

@@ -55,6 +55,20 @@ def full_sdf_loss(sdf, target_sdf, free_space_factor=5.0):
     return free, sdf - target_sdf
 
 
+def tsdf_loss(sdf, target_sdf, trunc_dist):
+    """TSDF-style residuals: sdf - 1 in free space, sdf - target / trunc_dist in the band (loss.py:167-175)."""
+    return sdf - torch.ones_like(sdf), sdf - target_sdf / trunc_dist
+
+
+def approx_loss(full_loss, binary_masks, W, H, factor=8):
+    """[F,H,W] loss image and pixel mask -> [F,factor,factor] block means over the sampled pixels
+    (loss.py:208-218).  Dense-image form kept for callers that have such images; Trainer.step() uses K5."""
+    hb, wb = H // factor, W // factor
+    sums = full_loss.view(-1, factor, hb, factor, wb).sum(dim=(2, 4))
+    n = binary_masks.view(-1, factor, hb, factor, wb).sum(dim=(2, 4))
+    return sums / torch.where(n == 0, torch.ones_like(n), n)
+
+
 def sdf_loss(sdf, bounds, t, loss_type="L1"):
     """Free-space loss where bounds > t, direct supervision inside the truncation band (loss.py:122-145)."""
     free, trunc = full_sdf_loss(sdf, bounds)

@@ -26,3 +26,9 @@ def render_normals(T_WC, render_depth, sdf_map, dirs_C):
     n_W = -g / (g.norm(dim=1, keepdim=True) + 1e-4)
     n_C = (R_WC.inverse() * n_W[..., None, :]).sum(dim=-1)
     return n_C.view(render_depth.shape[0], render_depth.shape[1], 3)
+
+
+def render_weighted(weights, vals, dim=-1, normalise=False):
+    """Weighted sum along `dim`, optionally divided by the number of samples (render.py:60-71)."""
+    out = (weights * vals).sum(dim=dim)
+    return out / weights.size(dim) if normalise else out

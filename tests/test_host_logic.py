@@ -50,3 +50,91 @@ def test_checkpoint_structure_matches_reference_files():
     ref_opt = torch.optim.AdamW(m.parameters(), lr=0.5, weight_decay=0.5)
     ref_opt.load_state_dict(ck["optimizer_state_dict"])
     assert ref_opt.param_groups[0]["lr"] == 0.0013 and float(ref_opt.state[list(m.parameters())[0]]["step"]) == 2.0
+
+
+# ---- host helpers vs the reference (tests/golden/make_golden_host.py) ---------------------------------------------
+def _close(a, b, tol=1e-6):
+    a = torch.as_tensor(a)
+    b = torch.as_tensor(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    nan = torch.isnan(b)
+    assert torch.equal(torch.isnan(a), nan)
+    assert torch.allclose(a[~nan].double(), b[~nan].double(), atol=tol, rtol=tol)
+
+
+def test_transform_helpers_match_reference():
+    import numpy as np
+    from isdf_b200.geometry import transform as T
+    g = load("host.pt")
+    H, W, cam = 12, 16, (20.0, 21.0, 7.5, 5.5)
+    _close(T.ray_dirs_C(2, H, W, *cam, "cpu", "z"), g["ray_dirs_z"])
+    _close(T.ray_dirs_C(1, H, W, *cam, "cpu", "euclidean"), g["ray_dirs_e"])
+    dirs = g["ray_dirs_z"].view(2, -1, 3)[0, :40]
+    Tw = torch.stack([C.synthetic_pose(k % 5) for k in range(40)])
+    for mine, ref in zip(T.origin_dirs_W(Tw, dirs), g["origin_dirs_W"]):
+        _close(mine, ref)
+    for mine, ref in zip(T.origin_dirs_W(Tw[3:4], g["ray_dirs_z"].view(2, -1, 3)[:1]), g["origin_dirs_W_one_pose"]):
+        _close(mine, ref)
+    depth = C.synthetic_depth(2, H, W)
+    depth[3, 4] = float("nan")
+    _close(T.pointcloud_from_depth_torch(depth, *cam), g["pc_torch"])
+    _close(T.pointcloud_from_depth_torch(depth, *cam, depth_type="euclidean", skip=2), g["pc_torch_e_skip2"])
+    _close(T.pointcloud_from_depth(depth.numpy(), *cam), g["pc_np"])
+    _close(T.backproject_pointclouds(np.stack([depth.numpy(), 2 * depth.numpy()]), *cam), g["backproject"])
+    pts = torch.randn(50, 3, generator=C.gen(81))      # the golden script's first draw from gen(81)
+    ext, cen = T.pc_bounds(pts.numpy())
+    _close(ext, g["pc_bounds"][0]); _close(cen, g["pc_bounds"][1])
+    n = T.estimate_pointcloud_normals(T.pointcloud_from_depth_torch(C.synthetic_depth(1, 24, 32), 30., 30., 15.5, 11.5))
+    _close(n, g["normals"], tol=1e-5)
+    _close(T.normalize(np.array([3.0, -4.0, 12.0])), g["normalize"])
+
+
+def test_loss_and_render_helpers_match_reference():
+    from isdf_b200.modules import loss as L, render as R, sample as S
+    g = load("host.pt")
+    batch, _ = C.loss_batch(82, 20)
+    b, gv = L.bounds_ray(batch["depth_sample"], batch["z_vals"], batch["dirs_C_sample"], batch["T_WC_sample"], True)
+    _close(b, g["bounds_ray"][0]); _close(gv, g["bounds_ray"][1])
+    sdf = g["sdf"]
+    for lt in ("L1", "L2"):
+        mat, free = L.sdf_loss(sdf, b, 0.29365022, loss_type=lt)
+        _close(mat, g["sdf_loss_" + lt][0]); assert torch.equal(free, g["sdf_loss_" + lt][1])
+    for mine, ref in zip(L.full_sdf_loss(sdf, b), g["full_sdf_loss"]):
+        _close(mine, ref)
+    for mine, ref in zip(L.tsdf_loss(sdf, b, 0.3), g["tsdf_loss"]):
+        _close(mine, ref)
+    gq = C.gen(81)
+    torch.randn(50, 3, generator=gq); torch.randn(20, 27, generator=gq)         # replay the golden script's draws
+    gl, ek = torch.rand(20, 27, generator=gq), torch.rand(20, 27, generator=gq)
+    mat, free = L.sdf_loss(sdf, b, 0.29365022, loss_type="L1")
+    tot, tot_mat, losses = L.tot_loss(mat.clone(), gl, ek, free, b, 0.1, 5.38344020, 0.018, 0.268)
+    _close(tot, g["tot_loss"][0]); _close(tot_mat, g["tot_loss"][1])
+    assert list(losses) == list(g["tot_loss"][2])                                  # same keys, same order (train.py:138,215)
+    for k, v in g["tot_loss"][2].items():
+        assert abs(float(losses[k]) - v) < 1e-6
+    full, masks = torch.rand(3, 16, 24, generator=gq), (torch.rand(3, 16, 24, generator=gq) < 0.2).float()
+    _close(L.approx_loss(full * masks, masks.clone(), 24, 16, 8), g["approx_loss"])
+    w, v = torch.rand(5, 9, generator=gq), torch.rand(5, 9, generator=gq)
+    _close(R.render_weighted(w, v), g["render_weighted"][0]); _close(R.render_weighted(w, v, normalise=True), g["render_weighted"][1])
+    torch.manual_seed(9)
+    _close(S.stratified_sample(0.07, 5.0, 6, "cpu", 11), g["strat_scalar"])
+    torch.manual_seed(9)
+    _close(S.stratified_sample(0.07, torch.linspace(1, 3, 6), 6, "cpu", 11), g["strat_tensor"])
+
+
+def test_framedata_append_and_replace_match_reference():
+    import numpy as np
+    from isdf_b200.datasets.data_util import FrameData
+    g = load("host.pt")["framedata"]
+    fd = FrameData()
+    for (k, rep), ref in zip(((0, False), (1, False), (2, True), (3, False), (4, True)), g):
+        d_ = FrameData(frame_id=np.array([k]), im_batch=torch.full((1, 2, 3, 3), float(k)), im_batch_np=np.full((1, 2, 3, 3), k, np.uint8),
+                       depth_batch=torch.full((1, 2, 3), float(k)), depth_batch_np=np.full((1, 2, 3), k, np.float32),
+                       T_WC_batch=torch.eye(4)[None] * k, T_WC_batch_np=np.eye(4, dtype=np.float32)[None] * k,
+                       normal_batch=torch.full((1, 2, 3, 3), float(k)))
+        fd.add_frame_data(d_, replace=rep)
+        n, fid, dep, im, favg, tnp = ref
+        assert len(fd) == n and np.array_equal(fd.frame_id, fid)
+        assert torch.equal(fd.depth_batch[:, 0, 0], dep) and np.array_equal(fd.im_batch_np[:, 0, 0, 0], im)
+        assert torch.equal(fd.frame_avg_losses, favg) and np.array_equal(fd.T_WC_batch_np[:, 0, 0], tnp)
+        assert fd.normal_batch.shape == (n, 2, 3, 3) and fd.im_batch.shape == (n, 2, 3, 3)
