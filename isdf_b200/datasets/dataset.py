@@ -80,6 +80,43 @@ class ReplicaDataset:
         return {"image": image, "depth": depth, "T": T}
 
 
+class ScanNetDataset:
+    """ScanNet layout of the reference (datasets/dataset.py:74-121): <root>/frames/color/<i>.jpg,
+    <root>/frames/depth/<i>.png (uint16), poses as N x 16 rows in `traj_file`."""
+
+    def __init__(self, root_dir, traj_file, rgb_transform=None, depth_transform=None, col_ext=".jpg",
+                 noisy_depth=None, distortion_coeffs=None, camera_matrix=None):
+        self.root_dir = root_dir
+        self.rgb_dir = os.path.join(root_dir, "frames", "color")
+        self.depth_dir = os.path.join(root_dir, "frames", "depth")
+        self.Ts = None if traj_file is None else np.loadtxt(traj_file).reshape(-1, 4, 4)
+        self.rgb_transform, self.depth_transform, self.col_ext = rgb_transform, depth_transform, col_ext or ".jpg"
+
+    def __len__(self):
+        return self.Ts.shape[0]
+
+    def __getitem__(self, idx):
+        import cv2
+        idx = int(idx)
+        depth = cv2.imread(os.path.join(self.depth_dir, "%d.png" % idx), -1)
+        image = cv2.imread(os.path.join(self.rgb_dir, "%d%s" % (idx, self.col_ext)))
+        if depth is None or image is None:
+            raise FileNotFoundError("missing ScanNet frame %d under %s" % (idx, self.root_dir))
+        T = self.Ts[idx] if self.Ts is not None else None
+        if self.rgb_transform:
+            image = self.rgb_transform(image)
+        if self.depth_transform:
+            depth = self.depth_transform(depth)
+        return {"image": image, "depth": depth, "T": T}
+
+
+def read_scannet_intrinsics(file):
+    """fx, fy, cx, cy, H, W of the DEPTH camera from a ScanNet scene .txt (trainer.py:335-346)."""
+    info = dict(line.split(' = ') for line in open(file).read().splitlines() if ' = ' in line)
+    return (float(info['fx_depth']), float(info['fy_depth']), float(info['mx_depth']), float(info['my_depth']),
+            int(info['depthHeight']), int(info['depthWidth']))
+
+
 def depth_scale_filter(inv_scale, max_depth):
     """uint16 depth -> metres, far values zeroed (reference datasets/image_transforms.py:18-38)."""
     def f(depth):

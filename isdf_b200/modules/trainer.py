@@ -252,10 +252,7 @@ class Trainer:
         self.n_strat_samples, self.n_surf_samples = sp["n_strat_samples"], sp["n_surf_samples"]
 
     def set_scannet_cam_params(self, file):
-        info = dict(line.split(' = ') for line in open(file).read().splitlines() if ' = ' in line)
-        self.fx, self.fy = float(info['fx_depth']), float(info['fy_depth'])
-        self.cx, self.cy = float(info['mx_depth']), float(info['my_depth'])
-        self.H, self.W = int(info['depthHeight']), int(info['depthWidth'])
+        self.fx, self.fy, self.cx, self.cy, self.H, self.W = ds.read_scannet_intrinsics(file)
 
     def set_cam(self):
         for tag, f in (("vis", 16), ("vis_up", 8)):
@@ -329,9 +326,14 @@ class Trainer:
                                                    col_ext=".png" if fmt == "replicaCAD" else ".jpg",
                                                    noisy_depth=self.noisy_depth if fmt == "replicaCAD" else False)
             self._depth_is_metric = True
+        elif fmt == "ScanNet":
+            self.up = np.array([0., 0., 1.])
+            self.scene_dataset = ds.ScanNetDataset(self.scannet_dir, traj_file=self.traj_file, rgb_transform=ds.bgr_to_rgb,
+                                                   depth_transform=depth_tf, col_ext=".jpg")
+            self._depth_is_metric = True
         else:
-            raise NotImplementedError("dataset format %r: only 'synthetic', 'replicaCAD' and 'replica' readers are "
-                                      "provided (dataset IO is outside the hot path)" % fmt)
+            raise NotImplementedError("dataset format %r: only 'synthetic', 'replicaCAD', 'replica' and 'ScanNet' readers "
+                                      "are provided (live / ROS ingest is outside the hot path)" % fmt)
         if self.incremental is False:
             if self.indices is None:
                 n_views = self.config["dataset"].get("n_views", 0)

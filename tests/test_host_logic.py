@@ -138,3 +138,36 @@ def test_framedata_append_and_replace_match_reference():
         assert torch.equal(fd.depth_batch[:, 0, 0], dep) and np.array_equal(fd.im_batch_np[:, 0, 0, 0], im)
         assert torch.equal(fd.frame_avg_losses, favg) and np.array_equal(fd.T_WC_batch_np[:, 0, 0], tnp)
         assert fd.normal_batch.shape == (n, 2, 3, 3) and fd.im_batch.shape == (n, 2, 3, 3)
+
+
+def test_scannet_reader_and_intrinsics(tmp_path):
+    """configs[2] (ScanNet): the reader of the reference's on-disk layout (datasets/dataset.py:74-121) and the
+    depth-camera intrinsics parser (trainer.py:335-346); depth in metres, far values zeroed (image_transforms.py)."""
+    import cv2
+    import numpy as np
+    from isdf_b200.datasets import dataset as ds
+    root = tmp_path / "scene0010_00"
+    (root / "frames" / "color").mkdir(parents=True)
+    (root / "frames" / "depth").mkdir(parents=True)
+    rng = np.random.default_rng(3)
+    depths, poses = [], []
+    for i in range(3):
+        d = rng.integers(0, 6000, size=(48, 64)).astype(np.uint16)
+        d[0, 0] = 20000                                               # 20 m -> zeroed by the depth filter (max 12 m)
+        cv2.imwrite(str(root / "frames" / "depth" / ("%d.png" % i)), d)
+        cv2.imwrite(str(root / "frames" / "color" / ("%d.jpg" % i)), np.full((96, 128, 3), (10 * i, 100, 200), np.uint8))
+        depths.append(d)
+        poses.append(C.synthetic_pose(i).numpy().reshape(-1))
+    np.savetxt(str(root / "traj.txt"), np.array(poses))
+    (root / "scene0010_00.txt").write_text("colorHeight = 968\ncolorWidth = 1296\ndepthHeight = 480\ndepthWidth = 640\n"
+                                           "fx_depth = 577.870605\nfy_depth = 577.870605\nmx_depth = 319.5\nmy_depth = 239.5\n")
+    assert ds.read_scannet_intrinsics(str(root / "scene0010_00.txt")) == (577.870605, 577.870605, 319.5, 239.5, 480, 640)
+    rd = ds.ScanNetDataset(str(root), str(root / "traj.txt"), rgb_transform=ds.bgr_to_rgb,
+                           depth_transform=ds.depth_scale_filter(1.0 / 1000.0, 12.0))
+    assert len(rd) == 3
+    s = rd[2]
+    ref = depths[2].astype(np.float32) / 1000.0
+    ref[ref > 12.0] = 0.0
+    assert s["depth"].dtype == np.float32 and np.allclose(s["depth"], ref) and s["depth"][0, 0] == 0.0
+    assert s["image"].shape == (96, 128, 3) and abs(int(s["image"][5, 5, 0]) - 200) <= 3       # BGR -> RGB
+    assert np.allclose(s["T"], C.synthetic_pose(2).numpy())
