@@ -3,6 +3,7 @@ fixtures produced by the unmodified reference (tests/golden/make_golden_infer.py
 import io
 import os
 
+import pytest
 import torch
 
 from tests.golden import common as C
@@ -171,3 +172,20 @@ def test_scannet_reader_and_intrinsics(tmp_path):
     assert s["depth"].dtype == np.float32 and np.allclose(s["depth"], ref) and s["depth"][0, 0] == 0.0
     assert s["image"].shape == (96, 128, 3) and abs(int(s["image"][5, 5, 0]) - 200) <= 3       # BGR -> RGB
     assert np.allclose(s["T"], C.synthetic_pose(2).numpy())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/isdf"), reason="needs the reference checkout (build container only)")
+def test_alias_package_layers_over_the_reference_checkout():
+    """with this repo BEFORE the reference on sys.path, the drivers' imports resolve --
+    replaced modules here, everything else (isdf.visualisation, isdf.eval.plot_utils, missing names) in the reference."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "dropin_check.py")], capture_output=True, text=True,
+                         timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    out = res.stdout
+    assert "trainer from %s" % os.path.join(root, "isdf_b200", "modules", "trainer.py") in out
+    assert "visualisation from /root/reference/isdf/visualisation/__init__.py" in out
+    assert "accuracy_comp (fallback): isdf_reference.eval.metrics" in out
+    assert "isdf.eval.plot_utils from /root/reference/isdf/eval/plot_utils.py" in out
