@@ -34,7 +34,9 @@ from . import embedding, fc_map, render, sample
 
 _OUT_OF_SCOPE = ("view_sdf", "latest_frame_vis", "update_vis_vars", "frames_vis", "draw_3D", "draw_obj_3D",
                  "obj_slices_vis", "write_slices", "write_mesh", "mesh_rec", "eval_fixed", "eval_sdf",
-                 "eval_object_sdf", "eval_mesh", "compute_slices")
+                 "eval_object_sdf", "eval_mesh", "compute_slices", "keyframe_vis", "slices_vis", "render_depth_vis",
+                 "render_normals_vis", "to_topdown", "load_gt_sdf", "check_gt_sdf", "eval_sdf_visible", "eval_sdf_volume",
+                 "eval_traj_cost")
 
 
 class FusedAdamW:
