@@ -55,6 +55,39 @@ def test_two_rank_gradient_allreduce_matches_single_process(tmp_path):
     assert err < 1e-5, err                                       # equal shard sizes: mean of means == global mean
 
 
+class _FakeEngine:
+    """Just enough of Engine for GradExchange.__init__ to reach the symmetric-memory allocation."""
+
+    def grad_buffer(self):
+        return torch.zeros(1000)
+
+    def set_grad_exchange(self, *a):
+        raise AssertionError("must not be reached on a CPU device")
+
+
+def _fallback_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # no NVLink multicast here: construction fails on every rank, the collective vote says "use the all-reduce"
+    ex, err = parallel.try_grad_exchange(_FakeEngine(), torch.device("cpu"))
+    g = torch.full((8,), float(rank + 1))
+    parallel.allreduce_sum_(g)
+    torch.save(dict(ex=ex is None, err=repr(err), g=g), os.path.join(out_dir, "f%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_exchange_setup_falls_back_collectively(tmp_path):
+    """try_grad_exchange is a COLLECTIVE decision: when the multicast exchange cannot be built, every rank learns it
+    (no rank waits in a rendezvous) and the NCCL / gloo all-reduce path carries on."""
+    world = 2
+    port = 29950 + (os.getpid() % 40)
+    mp.spawn(_fallback_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), "f%d.pt" % r), weights_only=False) for r in range(world)]
+    assert all(r["ex"] for r in res) and all(r["err"] != "None" for r in res)
+    assert torch.equal(res[0]["g"], torch.full((8,), 3.0)) and torch.equal(res[1]["g"], res[0]["g"])
+
+
 def test_keyframe_sharding_is_a_partition():
     frames = list(range(23))
     parts = [parallel.shard_keyframes(frames, r, 4) for r in range(4)]
