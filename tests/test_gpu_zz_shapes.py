@@ -1,0 +1,50 @@
+"""GPU parity at the model shapes of the other shipped / BASELINE configs: wide MLP 512x(4+4)
+(BASELINE configs[4]), realsense E = 381 (n_embed_funcs 8), franka E = 465 with hidden_layers_block 3.  These run on
+the CUDA-core fp32 path (the tcgen05 kernel is specialised to hidden 256 / E <= 256 and must refuse them loudly);
+checked against the fp64 oracle like the default shape.  (File name sorts last on purpose: the default-shape suites
+run first.)"""
+import pytest
+import torch
+
+from oracle import isdf_oracle as O
+from tests.golden import common as C
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+SHAPES = [("wide_512x8", 6, 512, 4), ("realsense_E381", 9, 256, 2), ("franka_E465_block3", 11, 256, 3)]
+
+
+def _case(n_freqs, hidden, block, R=48, S=16):
+    cfg = O.default_cfg(n_freqs=n_freqs, hidden=hidden, block=block, noise_std=0.05, n_strat=S - 8, n_surf=8)
+    sd = C.golden_weights(5, E=3 + 42 * n_freqs, H=hidden, block=block, gain=1.2)
+    batch, noise = C.loss_batch(9, R, S=S)
+    return cfg, sd, batch, noise
+
+
+@pytest.mark.parametrize("tag,n_freqs,hidden,block", SHAPES, ids=[s[0] for s in SHAPES])
+def test_fp32_path_matches_oracle_at_other_shapes(tag, n_freqs, hidden, block):
+    cfg, sd, batch, noise = _case(n_freqs, hidden, block)
+    eng = P.make_engine(DEV, cfg, "fp32", max_points=512)          # 768 samples: two internal chunks
+    assert eng.embedding_size == 3 + 42 * n_freqs and eng.n_params == sum(v.numel() for v in sd.values())
+    out = P.run_train(eng, sd, batch, noise, cfg, DEV)
+    ref = P.oracle_train(sd, batch, noise, cfg)
+    e = P.compare_train(out, ref)
+    assert e["sdf"] < 5e-6 and e["g"] < 1e-4, e
+    assert e["total_loss"] < 5e-5 and e["sdf_loss"] < 5e-5, e
+    assert e["grad_max_rel_fro"] < 1e-3, e
+    # forward-only and forward + input gradient on ragged sizes
+    x = batch["pc"].reshape(-1, 3)[:301].to(DEV).contiguous()
+    layers = [(w.double(), b.double()) for w, b in O.layers_from_state_dict(sd, block)]
+    sdf_ref = O.sdf_forward(layers, x.cpu().double(), cfg)
+    sdf, g = eng.forward(x, want_grad=True)
+    assert P.rel(sdf.cpu(), sdf_ref) < 5e-6 and P.rel(eng.forward(x).cpu(), sdf_ref) < 5e-6
+    assert P.rel(g.cpu(), out["g"].reshape(-1, 3)[:301]) < 1e-4
+
+
+@pytest.mark.parametrize("tag,n_freqs,hidden,block", SHAPES[:2], ids=[s[0] for s in SHAPES[:2]])
+def test_tensor_core_path_refuses_other_shapes_loudly(tag, n_freqs, hidden, block):
+    from isdf_b200 import _lib
+    cfg, _, _, _ = _case(n_freqs, hidden, block)
+    with pytest.raises(_lib.IsdfbError, match="tensor-core path supports hidden=256"):
+        P.make_engine(DEV, cfg, "bf16x3", max_points=512)

@@ -191,3 +191,20 @@ def test_adamw_matches_torch():
         gr = torch.randn(1000, generator=g) * 0.01
         p, m, v = O.adamw_update(p, gr, m, v, it + 1, 0.0013, 0.012)
         assert torch.allclose(p, gold[it], atol=1e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("n_freqs,hidden,block", [(6, 512, 4), (9, 256, 2), (11, 256, 3)])
+def test_oracle_formulations_agree_at_other_model_shapes(n_freqs, hidden, block):
+    """The shapes of BASELINE configs[4] and of the realsense / franka configs: the explicit
+    sweeps equal autograd in fp64 there too (they are the oracle of tests/test_gpu_zz_shapes.py)."""
+    cfg = O.default_cfg(n_freqs=n_freqs, hidden=hidden, block=block, noise_std=0.05, n_strat=8, n_surf=8)
+    sd = C.golden_weights(5, E=3 + 42 * n_freqs, H=hidden, block=block, gain=1.2)
+    layers = [(w.double(), b.double()) for w, b in O.layers_from_state_dict(sd, block)]
+    batch, noise = C.loss_batch(9, 6, S=16)
+    batch = {k: v.double() for k, v in batch.items()}
+    a = O.step_autograd(layers, batch, cfg, noise.double())
+    s = O.step_sweeps(layers, batch, cfg, noise.double())
+    assert len(a["grads"]) == 2 * (2 * block + 3)
+    assert (a["sdf"] - s["sdf"]).abs().max() < 1e-12 and (a["g"] - s["g"]).abs().max() < 1e-12
+    for ga, gs in zip(a["grads"], s["grads"]):
+        assert (ga - gs).abs().max() <= 1e-10 * max(1.0, float(ga.abs().max()))
