@@ -305,6 +305,11 @@ def main():
                 roof["traffic"] = json.load(open(traffic_file)).get(args.precision, {}).get(args.workload)
             except Exception:
                 pass
+        if roof["traffic"]:
+            # the same launch against the HBM roofline (ncu DRAM bytes / live kernel time): the kernel's second bound
+            hbm_peak = peaks.get("hbm_gbs", PEAKS_FALLBACK["hbm_gbs"])
+            roof["hbm_achieved_gbs"] = roof["traffic"] / (chain_ms * 1e-3) / 1e9
+            roof["hbm_frac"] = roof["hbm_achieved_gbs"] / hbm_peak
 
     # ---------------- CPU baseline (oracle port, bounded sample) ----------------
     cpu = None
