@@ -38,7 +38,11 @@ typedef enum {
 typedef enum {
   ISDFB_PREC_FP32 = 0,       /* fp32 CUDA-core path (exact-parity mode, also the on-device check) */
   ISDFB_PREC_BF16X3 = 1,     /* tcgen05 kind::f16, bf16 hi/lo split, 3 MMAs per product (~fp32) */
-  ISDFB_PREC_BF16 = 2        /* tcgen05 kind::f16, single bf16 pass (fast mode) */
+  ISDFB_PREC_BF16 = 2,       /* tcgen05 kind::f16, single bf16 pass (fast mode) */
+  ISDFB_PREC_BF16X3G = 3     /* as BF16X3 for every product of the sweeps S1..S4 (sdf, d sdf/dx, losses identical), but
+                                the operands handed to the weight-gradient products, the S3 read-back of delta_l and
+                                zbar2_l are single bf16: half the per-point side state in HBM; weight gradients carry
+                                bf16 operand rounding (rel. Frobenius ~1e-3).  The default of the Python layer. */
 } isdfb_precision;
 
 /* Model description: fc_map.py:63-111 (SDFMap.__init__), embedding.py:25-66. */

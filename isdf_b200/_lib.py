@@ -10,8 +10,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libisdf_b200.so")
 
-PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_BF16X3G = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "bf16x3g": PREC_BF16X3G}
 
 
 class ModelCfg(C.Structure):

@@ -71,7 +71,7 @@ int isdfb_create(const isdfb_model_cfg* cfg, int device, isdfb_ctx** out) {
   ctx->cfg = *cfg;
   int rc = build_layout(*cfg, &ctx->lay, g_isdfb_create_err, sizeof(g_isdfb_create_err));
   if (rc) { delete ctx; return rc; }
-  if (cfg->precision < ISDFB_PREC_FP32 || cfg->precision > ISDFB_PREC_BF16) {
+  if (cfg->precision < ISDFB_PREC_FP32 || cfg->precision > ISDFB_PREC_BF16X3G) {
     snprintf(g_isdfb_create_err, sizeof(g_isdfb_create_err), "unknown precision %d", cfg->precision);
     delete ctx; return ISDFB_ERR_ARG;
   }

@@ -67,6 +67,7 @@ struct EpiT {                       // per-thread / per-tile constants (thread o
   uint8_t *dwl_hi, *dwl_lo;         // dW-layout array 0 + tile + (p>>4) 8192 + (p&15) 16 + (2 jg) 256
   float* aux;                       // aux array 0 + tile + p*4 + (4 jg) 512        (floats)
   uint8_t* sig;                     // sigma16 layer 0 + tile + p*16 + (2 jg) 2048
+  uint8_t* zb2h;                    // lean: zbar2 (bf16) layer 0, same addressing as sig
   size_t dwl_stride, aux_stride, sig_stride;
   int p, kcol;                      // kcol = 16 jg
   int c0;                           // first K chunk of this CTA's rotated order (rot_kstep)
@@ -76,7 +77,8 @@ struct EpiOps { uint4 s, b0, b1, e0, e1; };   // side-array operands of one sub-
 struct EpiStepPtrs {                  // per-step pointers (thread offsets included)
   const uint8_t* sigp; uint8_t* sigw;
   const uint8_t *dhi, *dlo;           // delta_l (dW layout) for S3
-  float* zb2;                         // zbar2_l
+  float* zb2;                         // zbar2_l  (fp32 side array; strict mode)
+  uint8_t* zb2h;                      // zbar2_l  (bf16, sigma-image layout; lean mode)
   const float* part_in;               // partial sums consumed by this step
   float* part_out;                    // RAW: partial sums produced
   const float *bias, *wout;
@@ -88,10 +90,12 @@ __device__ __forceinline__ uint32_t sub_a(int c, int h) { return (uint32_t)(8 * 
 __device__ __forceinline__ uint32_t sub_d(int c, int h) { return (uint32_t)(8 * c + h) * 256u; }
 __device__ __forceinline__ uint32_t sub_x(int c, int h) { return (uint32_t)(16 * c + 2 * h) * 512u; }
 
-template <int kPasses>
+// kLean: the weight-gradient operands (dW layout) keep only their bf16 hi part -- the products of S1..S4 themselves
+// stay hi/lo (A image), so sdf, d sdf/dx and the loss are unchanged; only dW sees the rounding.
+template <int kPasses, bool kLean>
 __device__ __forceinline__ void put8(const EpiT& T, const float* x, int c, int h, bool to_a, int dwl_arr) {
   uint4 hi, lo;
-  if (kPasses == 3) split8(x, hi, lo); else hi = pack8_hi(x);
+  if (kPasses == 3 && (to_a || !kLean)) split8(x, hi, lo); else hi = pack8_hi(x);
   if (to_a && !(T.ablate & 32)) {
     *reinterpret_cast<uint4*>(T.a_hi + sub_a(c, h)) = hi;
     if (kPasses == 3) *reinterpret_cast<uint4*>(T.a_lo + sub_a(c, h)) = lo;
@@ -99,11 +103,11 @@ __device__ __forceinline__ void put8(const EpiT& T, const float* x, int c, int h
   if (dwl_arr >= 0 && !(T.ablate & 1)) {
     const size_t off = (size_t)dwl_arr * T.dwl_stride + sub_d(c, h);
     *reinterpret_cast<uint4*>(T.dwl_hi + off) = hi;
-    if (kPasses == 3) *reinterpret_cast<uint4*>(T.dwl_lo + off) = lo;
+    if (kPasses == 3 && !kLean) *reinterpret_cast<uint4*>(T.dwl_lo + off) = lo;
   }
 }
 
-template <int EPI, int kPasses>
+template <int EPI, int kPasses, bool kLean>
 __device__ __forceinline__ void epi_load(const EpiStepPtrs& P, bool l_is_cat, int c, int h, EpiOps& o) {
   if (P.ablate & 8) return;
   auto ld = [&](const void* q) -> uint4 { return P.stream ? ld_stream(q) : *reinterpret_cast<const uint4*>(q); };
@@ -111,10 +115,14 @@ __device__ __forceinline__ void epi_load(const EpiStepPtrs& P, bool l_is_cat, in
     o.s = ld(P.sigp + sub_a(c, h));
   if (EPI == EPI_S3 || EPI == EPI_S3_LAST) {
     o.b0 = ld(P.dhi + sub_d(c, h));
-    if (kPasses == 3) o.b1 = ld(P.dlo + sub_d(c, h));
+    if (kPasses == 3 && !kLean) o.b1 = ld(P.dlo + sub_d(c, h));
   } else if (EPI == EPI_S4) {
-    o.b0 = ld(P.zb2 + sub_x(c, h));
-    o.b1 = ld(P.zb2 + sub_x(c, h) + 512);
+    if (kLean) {
+      o.b0 = ld(P.zb2h + sub_a(c, h));
+    } else {
+      o.b0 = ld(P.zb2 + sub_x(c, h));
+      o.b1 = ld(P.zb2 + sub_x(c, h) + 512);
+    }
   } else if (EPI == EPI_S2_END || ((EPI == EPI_S1 || EPI == EPI_S1_LAST) && l_is_cat)) {
     o.b0 = ld(P.part_in + sub_x(c, h));
     o.b1 = ld(P.part_in + sub_x(c, h) + 512);
@@ -136,7 +144,7 @@ __device__ __forceinline__ int rot_kstep(int ks, int rot) {
   return ((((ks >> 2) + (rot >> 2)) & 3) << 2) | (((ks & 3) + rot) & 3);
 }
 
-template <int EPI, int kPasses>
+template <int EPI, int kPasses, bool kLean>
 __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, const EpiStepPtrs& P, const EpiOps& o,
                                         float* v /* 8 accumulator columns of this sub-piece */, int c, int h, int l,
                                         bool l_is_cat, bool train, bool store_state, bool last_step, float sbar,
@@ -164,7 +172,7 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
     }
     if (store_state && !(T.ablate & 4)) *reinterpret_cast<uint4*>(P.sigw + sub_a(c, h)) = pack_unorm16x8(sg);
     if (EPI == EPI_S1) {
-      put8<kPasses>(T, hh, c, h, true, (train && l + 1 < args.L) ? args.arr_yh + l + 1 : -1);
+      put8<kPasses, kLean>(T, hh, c, h, true, (train && l + 1 < args.L) ? args.arr_yh + l + 1 : -1);
     } else {
       const float4 wa = ld4(P.wout + k0), wb = ld4(P.wout + k0 + 4);
       const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -177,14 +185,14 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
         acc.raw_acc = fmaf(hh[t], ww[t], acc.raw_acc);
         v[t] = args.scale_output * ww[t] * sg[t];          // delta_{L-1} = a_{L-1} * sigma
       }
-      put8<kPasses>(T, v, c, h, args.mode != TC_MODE_FWD, train ? args.arr_xd + l : -1);
+      put8<kPasses, kLean>(T, v, c, h, args.mode != TC_MODE_FWD, train ? args.arr_xd + l : -1);
     }
   } else if (EPI == EPI_S2) {
     float sg[8];
     unpack_unorm16x8(o.s, sg);
 #pragma unroll
     for (int t = 0; t < 8; ++t) v[t] *= sg[t];
-    put8<kPasses>(T, v, c, h, true, train ? args.arr_xd + l : -1);
+    put8<kPasses, kLean>(T, v, c, h, true, train ? args.arr_xd + l : -1);
   } else if (EPI == EPI_S2_END) {
     if (T.ablate & 64) { acc.gx += v[0]; return; }
     // PE Jacobian in the internal column order (tc_common.cuh): columns (2i, 2i+1) = (sin, cos) of pair i, so
@@ -213,7 +221,7 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
     float sg[8], dl[8], zb[8];
     unpack_unorm16x8(o.s, sg);
     unpack8(o.b0, dl);
-    if (kPasses == 3) {
+    if (kPasses == 3 && !kLean) {
       float t8[8];
       unpack8(o.b1, t8);
 #pragma unroll
@@ -231,10 +239,14 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
     }
     if (EPI == EPI_S3) {
       if (!(T.ablate & 2)) {
-        st4(P.zb2 + sub_x(c, h), zb[0], zb[1], zb[2], zb[3]);
-        st4(P.zb2 + sub_x(c, h) + 512, zb[4], zb[5], zb[6], zb[7]);
+        if (kLean) {
+          *reinterpret_cast<uint4*>(P.zb2h + sub_a(c, h)) = pack8_hi(zb);
+        } else {
+          st4(P.zb2 + sub_x(c, h), zb[0], zb[1], zb[2], zb[3]);
+          st4(P.zb2 + sub_x(c, h) + 512, zb[4], zb[5], zb[6], zb[7]);
+        }
       }
-      put8<kPasses>(T, v, c, h, true, (l + 1 < args.L) ? args.arr_ya + l + 1 : -1);
+      put8<kPasses, kLean>(T, v, c, h, true, (l + 1 < args.L) ? args.arr_ya + l + 1 : -1);
     } else {
       // v_blob = sbar * h_last + abar_last  (for d w_out);  A <- zbar_last = sbar c w_out sigma + zbar2
       const float4 ha = ld4(P.hlast + sub_x(c, h)), hb = ld4(P.hlast + sub_x(c, h) + 512);
@@ -247,22 +259,27 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
         vb[t] = fmaf(sbar, hh[t], v[t]);
         zb[t] = fmaf(sbar * args.scale_output * ww[t], sg[t], zb[t]);
       }
-      put8<kPasses>(T, vb, c, h, false, args.arr_v);
-      put8<kPasses>(T, zb, c, h, true, args.arr_xz + l);
+      put8<kPasses, kLean>(T, vb, c, h, false, args.arr_v);
+      put8<kPasses, kLean>(T, zb, c, h, true, args.arr_xz + l);
     }
   } else {   // EPI_S4
     float sg[8];
     unpack_unorm16x8(o.s, sg);
-    const float z2[8] = {__uint_as_float(o.b0.x), __uint_as_float(o.b0.y), __uint_as_float(o.b0.z), __uint_as_float(o.b0.w),
-                         __uint_as_float(o.b1.x), __uint_as_float(o.b1.y), __uint_as_float(o.b1.z), __uint_as_float(o.b1.w)};
+    float z2[8];
+    if (kLean) {
+      unpack8(o.b0, z2);
+    } else {
+      z2[0] = __uint_as_float(o.b0.x); z2[1] = __uint_as_float(o.b0.y); z2[2] = __uint_as_float(o.b0.z); z2[3] = __uint_as_float(o.b0.w);
+      z2[4] = __uint_as_float(o.b1.x); z2[5] = __uint_as_float(o.b1.y); z2[6] = __uint_as_float(o.b1.z); z2[7] = __uint_as_float(o.b1.w);
+    }
 #pragma unroll
     for (int t = 0; t < 8; ++t) v[t] = fmaf(v[t], sg[t], z2[t]);
-    put8<kPasses>(T, v, c, h, !last_step, args.arr_xz + l);
+    put8<kPasses, kLean>(T, v, c, h, !last_step, args.arr_xz + l);
   }
 }
 
 // one whole step of the epilogue for this thread (8 sub-pieces), operands fetched one sub-piece ahead
-template <int EPI, int kPasses, int kWide>
+template <int EPI, int kPasses, int kWide, bool kLean>
 __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T, const EpiStepPtrs& P, ChainSmemTail* tail,
                                          uint32_t d_tmem, uint32_t n, int l, bool train, bool store_state, bool last_step,
                                          float sbar, EpiAcc& acc, int lane) {
@@ -270,7 +287,7 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
   EpiOps oa, ob;
   oa.s = oa.b0 = oa.b1 = oa.e0 = oa.e1 = make_uint4(0, 0, 0, 0);
   ob = oa;
-  epi_load<EPI, kPasses>(P, l_is_cat, T.c0, 0, oa);         // overlaps the tail of this step's MMA
+  epi_load<EPI, kPasses, kLean>(P, l_is_cat, T.c0, 0, oa);         // overlaps the tail of this step's MMA
   mbar_wait(smem_u32(&tail->d_full[n & 1]), (n >> 1) & 1);
   tc_fence_after();
   if (EPI == EPI_RAW) {
@@ -285,20 +302,20 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
   if (kWide) {
     // operands of BOTH sub-pieces of the next chunk are requested before this chunk is processed: two sub-pieces
     // of lead on the side-state loads (L2 latency under load exceeds one) at the price of two more operand sets
-    epi_load<EPI, kPasses>(P, l_is_cat, T.c0, 1, ob);
+    epi_load<EPI, kPasses, kLean>(P, l_is_cat, T.c0, 1, ob);
 #pragma unroll 1
     for (int ci = 0; ci < 4; ++ci) {
       const int c = (ci + T.c0) & 3;
       EpiOps na = oa, nb = ob;
       if (ci < 3) {
-        epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 0, na);
-        epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 1, nb);
+        epi_load<EPI, kPasses, kLean>(P, l_is_cat, (c + 1) & 3, 0, na);
+        epi_load<EPI, kPasses, kLean>(P, l_is_cat, (c + 1) & 3, 1, nb);
       }
       float v[8];
       tmem_ld8(d_tmem + 64 * c + T.kcol, v);
-      epi_sub<EPI, kPasses>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      epi_sub<EPI, kPasses, kLean>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
       tmem_ld8(d_tmem + 64 * c + T.kcol + 8, v);
-      epi_sub<EPI, kPasses>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      epi_sub<EPI, kPasses, kLean>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
       if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
         fence_proxy_async_smem();
         __syncwarp();
@@ -318,12 +335,12 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
         }
         continue;
       }
-      epi_load<EPI, kPasses>(P, l_is_cat, c, 1, ob);
+      epi_load<EPI, kPasses, kLean>(P, l_is_cat, c, 1, ob);
       tmem_ld8(d_tmem + 64 * c + T.kcol, v);
-      epi_sub<EPI, kPasses>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
-      if (ci < 3) epi_load<EPI, kPasses>(P, l_is_cat, (c + 1) & 3, 0, oa);
+      epi_sub<EPI, kPasses, kLean>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      if (ci < 3) epi_load<EPI, kPasses, kLean>(P, l_is_cat, (c + 1) & 3, 0, oa);
       tmem_ld8(d_tmem + 64 * c + T.kcol + 8, v);
-      epi_sub<EPI, kPasses>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      epi_sub<EPI, kPasses, kLean>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
       if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
         fence_proxy_async_smem();
         __syncwarp();
@@ -334,7 +351,7 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
   tc_fence_before();
 }
 
-template <int kPasses, int kWide>
+template <int kPasses, int kWide, bool kLean>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_constant__ TcChainArgs args) {
   using Cfg = ChainCfg<kPasses>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -385,7 +402,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             auto pf_sig = [&](int l_) { bulk_prefetch_l2(args.sig16 + (size_t)l_ * args.sig16_stride + dwl_t, TC_DWL_TILE_BYTES); };
             auto pf_dwl = [&](int arr) {
               bulk_prefetch_l2(args.dwl_hi + (size_t)arr * args.dwl_stride + dwl_t, TC_DWL_TILE_BYTES);
-              if (kPasses == 3) bulk_prefetch_l2(args.dwl_lo + (size_t)arr * args.dwl_stride + dwl_t, TC_DWL_TILE_BYTES);
+              if (kPasses == 3 && !kLean) bulk_prefetch_l2(args.dwl_lo + (size_t)arr * args.dwl_stride + dwl_t, TC_DWL_TILE_BYTES);
+            };
+            auto pf_zb2 = [&](int l_) {
+              if (kLean) bulk_prefetch_l2(args.zb2h + (size_t)l_ * args.sig16_stride + dwl_t, TC_DWL_TILE_BYTES);
+              else pf_aux(args.arr_zb2 + l_);
             };
             switch (nx.epi) {
               case EPI_S1: case EPI_S1_LAST: if (nx.layer == args.ic) pf_aux(args.arr_part + 0); break;
@@ -396,7 +417,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
                 if (nx.layer == args.ic) pf_aux(args.arr_part + 2);
                 if (nx.epi == EPI_S3_LAST) pf_aux(args.arr_hlast);
                 break;
-              case EPI_S4: pf_sig(nx.layer); pf_aux(args.arr_zb2 + nx.layer); break;
+              case EPI_S4: pf_sig(nx.layer); pf_zb2(nx.layer); break;
               default: break;
             }
           }
@@ -478,6 +499,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
       T.dwl_lo = args.dwl_lo + dthr;
       T.aux = args.aux + (size_t)tile * TC_TILE_FLOATS + p * 4 + (4 * jg) * 512;
       T.sig = args.sig16 + (size_t)tile * TC_DWL_TILE_BYTES + p * 16 + (2 * jg) * 2048;
+      T.zb2h = args.zb2h + (size_t)tile * TC_DWL_TILE_BYTES + p * 16 + (2 * jg) * 2048;
       T.dwl_stride = args.dwl_stride; T.aux_stride = args.aux_stride; T.sig_stride = args.sig16_stride;
       float* e32_w = T.aux + (size_t)args.arr_e32 * args.aux_stride;
       auto chunk_ready = [&](int c) {
@@ -516,7 +538,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
           }
           v[jj] = va; v[jj + 1] = vb;
         }
-        put8<kPasses>(T, v, c, h, true, train ? args.arr_yh : -1);
+        put8<kPasses, kLean>(T, v, c, h, true, train ? args.arr_yh : -1);
         if (store_state && !(args.ablate & 2)) {
           st4(e32_w + sub_x(c, h), v[0], v[1], v[2], v[3]);
           st4(e32_w + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
@@ -541,6 +563,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         P.dhi = T.dwl_hi + (size_t)(args.arr_xd + l) * T.dwl_stride;
         P.dlo = T.dwl_lo + (size_t)(args.arr_xd + l) * T.dwl_stride;
         P.zb2 = T.aux + (size_t)(args.arr_zb2 + l) * T.aux_stride;
+        P.zb2h = T.zb2h + (size_t)l * T.sig_stride;
         P.part_in = T.aux + (size_t)(args.arr_part + (epi == EPI_S2_END ? 1 : ((epi == EPI_S3 || epi == EPI_S3_LAST) ? 2 : 0))) * T.aux_stride;
         P.part_out = T.aux + (size_t)(args.arr_part + st.aux) * T.aux_stride;
         P.bias = Wp + args.lay_b_off[l];
@@ -552,14 +575,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         EpiAcc acc = {0.f, 0.f, 0.f, 0.f};
         if (dbg) args.dbg_clock[1 + 2 * s] = clock64();
         switch (epi) {
-          case EPI_RAW:     epi_step<EPI_RAW, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S1:      epi_step<EPI_S1, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S1_LAST: epi_step<EPI_S1_LAST, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S2:      epi_step<EPI_S2, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S2_END:  epi_step<EPI_S2_END, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S3:      epi_step<EPI_S3, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S3_LAST: epi_step<EPI_S3_LAST, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          default:          epi_step<EPI_S4, kPasses, kWide>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_RAW:     epi_step<EPI_RAW, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S1:      epi_step<EPI_S1, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S1_LAST: epi_step<EPI_S1_LAST, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S2:      epi_step<EPI_S2, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S2_END:  epi_step<EPI_S2_END, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S3:      epi_step<EPI_S3, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S3_LAST: epi_step<EPI_S3_LAST, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          default:          epi_step<EPI_S4, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
         }
 
         if (dbg) args.dbg_clock[2 + 2 * s] = clock64();
@@ -654,7 +677,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
                 }
                 v[jj] = va; v[jj + 1] = vb;
               }
-              put8<kPasses>(T, v, c, h, true, args.arr_ya);
+              put8<kPasses, kLean>(T, v, c, h, true, args.arr_ya);
               if (h) chunk_ready(c);
             }
           }
@@ -688,11 +711,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
 
 int tc_chain_launch(isdfb_ctx* ctx, const TcChainArgs& args, int passes, int grid, cudaStream_t st) {
   if (passes == 3) {
-    if (args.wide) tc_chain_kernel<3, 1><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
-    else tc_chain_kernel<3, 0><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
+    if (args.lean) tc_chain_kernel<3, 1, true><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
+    else if (args.wide) tc_chain_kernel<3, 1, false><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
+    else tc_chain_kernel<3, 0, false><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
   } else {
-    if (args.wide) tc_chain_kernel<1, 1><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
-    else tc_chain_kernel<1, 0><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
+    if (args.wide) tc_chain_kernel<1, 1, false><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
+    else tc_chain_kernel<1, 0, false><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
   }
   ISDFB_LAUNCHED(ctx);
   ISDFB_CUDA_OK(ctx, cudaGetLastError());
@@ -700,9 +724,10 @@ int tc_chain_launch(isdfb_ctx* ctx, const TcChainArgs& args, int passes, int gri
 }
 
 int tc_chain_init(isdfb_ctx* ctx) {
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
+  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
   return ISDFB_OK;
 }

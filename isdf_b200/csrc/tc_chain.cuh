@@ -52,6 +52,9 @@ struct TcChainArgs {
   size_t aux_stride;         // floats between arrays
   uint8_t *dwl_hi, *dwl_lo;  // bf16 arrays [arr][tile][64 KB], dW layout
   uint8_t* sig16;            // sigma_l as unorm16, [layer][tile][64 KB], K-major image layout [f/8][p][8]
+  uint8_t* zb2h;             // lean mode: zbar2_l as bf16, same [layer][tile][64 KB] layout and stride as sig16
+  int32_t lean;              // 1: weight-gradient operands, the S3 read of delta_l and zbar2_l are single bf16 (precision
+                             //    "bf16x3g"): halves the per-point side state; sdf / d sdf/dx / loss are unaffected
   size_t sig16_stride;       // bytes between layers
   size_t dwl_stride;         // bytes between arrays
   int32_t arr_zb2, arr_part, arr_e32, arr_hlast;            // aux array indices

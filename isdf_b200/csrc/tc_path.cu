@@ -72,15 +72,16 @@ int tc_create(isdfb_ctx* ctx) {
   tc->units.u[L].w_off = lay.layer[ic].we_off;
   tc->units.u[L].ld = lay.Ep;
   tc->units.u[L].perm_half = pe_half;
+  const bool lean = ctx->cfg.precision == ISDFB_PREC_BF16X3G;
   tc->tiles_cap = ctx->cap / TC_TILE;
-  tc->n_aux = L + 5;
+  tc->n_aux = lean ? 5 : L + 5;              // part x3, e32, h_last (+ zbar2_l as fp32 unless lean)
   tc->n_dwl = 4 * L + 1;
   tc->aux_stride = (size_t)tc->tiles_cap * TC_TILE_FLOATS;
   tc->dwl_stride = (size_t)tc->tiles_cap * TC_DWL_TILE_BYTES;
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->w_img, (size_t)tc->n_units * 4 * TC_IMG_BYTES));
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->aux, tc->aux_stride * tc->n_aux * sizeof(float)));
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dwl_hi, tc->dwl_stride * tc->n_dwl));
-  ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->sig16, tc->dwl_stride * L));
+  ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->sig16, tc->dwl_stride * L * (lean ? 2 : 1)));     // lean: + zbar2_l (bf16)
   if (ctx->cfg.precision == ISDFB_PREC_BF16X3) ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dwl_lo, tc->dwl_stride * tc->n_dwl));
 
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->dw_counters, TC_MAX_JOBS * sizeof(int32_t)));
@@ -110,7 +111,10 @@ int tc_create(isdfb_ctx* ctx) {
     a.aux = tc->aux; a.aux_stride = tc->aux_stride;
     a.dwl_hi = tc->dwl_hi; a.dwl_lo = tc->dwl_lo; a.dwl_stride = tc->dwl_stride;
     a.sig16 = tc->sig16; a.sig16_stride = tc->dwl_stride;
-    a.arr_zb2 = 0; a.arr_part = L; a.arr_e32 = L + 3; a.arr_hlast = L + 4;
+    a.arr_part = 0; a.arr_e32 = 3; a.arr_hlast = 4; a.arr_zb2 = 5;      // zbar2 (fp32) last: absent in lean mode
+    a.lean = lean ? 1 : 0;
+    a.zb2h = lean ? tc->sig16 + tc->dwl_stride * L : nullptr;
+    if (lean) a.wide = 1;
     for (int i = 0; i < TC_H / 2; ++i) {      // pair i = (direction, octave) of internal columns 2i, 2i+1
       a.pair_d[i] = (uint8_t)(i < pe_half ? i / lay.n_freqs : 0);
       a.pair_f[i] = (uint8_t)(i < pe_half ? i % lay.n_freqs : 0);
@@ -166,7 +170,11 @@ static void prof_mark(TcState* tc, int i, int k, cudaStream_t st) {
   tc->ev_kind[i] = k;
 }
 
-static inline int passes_of(const isdfb_ctx* ctx) { return ctx->cfg.precision == ISDFB_PREC_BF16X3 ? 3 : 1; }
+static inline int passes_of(const isdfb_ctx* ctx) {
+  return (ctx->cfg.precision == ISDFB_PREC_BF16X3 || ctx->cfg.precision == ISDFB_PREC_BF16X3G) ? 3 : 1;
+}
+// the weight-gradient kernel reads single-bf16 operands in lean mode
+static inline int dw_passes_of(const isdfb_ctx* ctx) { return ctx->cfg.precision == ISDFB_PREC_BF16X3 ? 3 : 1; }
 
 int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n, float* sdf,
                float* grad, cudaStream_t st) {
@@ -257,7 +265,7 @@ int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* 
       ISDFB_CUDA_OK(ctx, cudaStreamWaitEvent(tc->side, tc->ev_fork, 0));
       d.tile0 = 0; d.n_tiles = tc->num_sms;
       const int rest = total_tiles - tc->num_sms;
-      rc = tc_dw_launch(ctx, d, passes_of(ctx), tc->num_sms - rest > 14 ? tc->num_sms - rest : 14, tc->side);
+      rc = tc_dw_launch(ctx, d, dw_passes_of(ctx), tc->num_sms - rest > 14 ? tc->num_sms - rest : 14, tc->side);
       if (rc) return rc;
       ISDFB_CUDA_OK(ctx, cudaEventRecord(tc->ev_join, tc->side));
       a.tile0 = tc->num_sms; a.n_tiles = rest;
@@ -265,7 +273,7 @@ int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* 
       if (rc) return rc;
       ISDFB_CUDA_OK(ctx, cudaStreamWaitEvent(st, tc->ev_join, 0));
       d.tile0 = tc->num_sms; d.n_tiles = rest;
-      rc = tc_dw_launch(ctx, d, passes_of(ctx), tc->num_sms, st);
+      rc = tc_dw_launch(ctx, d, dw_passes_of(ctx), tc->num_sms, st);
       if (rc) return rc;
     } else {
       const int grid = a.n_tiles < tc->num_sms ? a.n_tiles : tc->num_sms;
@@ -273,7 +281,7 @@ int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* 
       if (rc) return rc;
       prof_mark(tc, pi, 1, st);
       d.tile0 = 0; d.n_tiles = total_tiles;
-      rc = tc_dw_launch(ctx, d, passes_of(ctx), tc->num_sms, st);
+      rc = tc_dw_launch(ctx, d, dw_passes_of(ctx), tc->num_sms, st);
       if (rc) return rc;
       prof_mark(tc, pi, 2, st);
     }

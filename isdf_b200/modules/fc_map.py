@@ -13,7 +13,9 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import DEFAULT_PRECISION
+import warnings
+
+from .. import DEFAULT_PRECISION, _lib
 from ..engine import Engine
 
 
@@ -76,6 +78,7 @@ class SDFMap(nn.Module):
         self.precision = os.environ.get("ISDFB_PRECISION", DEFAULT_PRECISION)
         self.max_points = int(os.environ.get("ISDFB_MAX_POINTS", 32768))
         self._engine = None
+        self._engine_precision = self._engine_tr_key = None
         self._flat = None
         self._packed_sig = None
 
@@ -105,11 +108,23 @@ class SDFMap(nn.Module):
     def engine(self):
         flat = self.flat_parameters()
         dev = flat.device
-        if self._engine is None or self._engine.device != dev or self._engine.precision != self.precision:
-            pe = self.positional_encoding
-            self._engine = Engine(dev, pe.n_freqs, self.hidden_size, self.hidden_layers_block, pe.scale,
-                                  self.scale_output, transform=pe.transform, precision=self.precision,
-                                  max_points=self.max_points)
+        pe = self.positional_encoding
+        tr_key = pe.transform          # identity, not value: this runs on every call and must not touch the device
+        if (self._engine is None or self._engine.device != dev or self._engine_precision != self.precision
+                or self._engine_tr_key is not tr_key):
+            try:
+                self._engine = Engine(dev, pe.n_freqs, self.hidden_size, self.hidden_layers_block, pe.scale,
+                                      self.scale_output, transform=pe.transform, precision=self.precision,
+                                      max_points=self.max_points)
+            except _lib.IsdfbError as e:
+                if self.precision == "fp32" or "tensor-core path supports" not in str(e):
+                    raise
+                # shapes the tcgen05 kernels do not take run on the CUDA-core fp32 kernels of the same library
+                warnings.warn("isdf_b200: %s -- using precision 'fp32' (CUDA-core kernels) for this model" % e)
+                self._engine = Engine(dev, pe.n_freqs, self.hidden_size, self.hidden_layers_block, pe.scale,
+                                      self.scale_output, transform=pe.transform, precision="fp32",
+                                      max_points=self.max_points)
+            self._engine_precision, self._engine_tr_key = self.precision, tr_key
             self._packed_sig = None
         sig = (flat.data_ptr(), tuple(p._version for p in self.parameters()))
         if sig != self._packed_sig:
@@ -127,7 +142,7 @@ class SDFMap(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_engine", "_flat", "_packed_sig"):
+            if k in ("_engine", "_flat", "_packed_sig", "_engine_precision", "_engine_tr_key"):
                 new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)

@@ -101,7 +101,14 @@ class FusedAdamW:
                 self.exp_avg_sq[off:off + n] = st["exp_avg_sq"].reshape(-1).to(self.exp_avg.device)
                 self.step_count = int(float(st["step"]))
             off += n
-        self._dev_step_engine = None
+        # the device-side counter (read by captured graphs) follows the restored count immediately: a cached step
+        # graph keeps replaying after a load, and the moments above were updated in place
+        eng = self.sdf_map._engine
+        if eng is not None:
+            eng.adamw_set_step(self.step_count)
+            self._dev_step_engine = eng
+        else:
+            self._dev_step_engine = None
 
 
 class Trainer:
@@ -154,8 +161,9 @@ class Trainer:
         self.active_idxs = None
         self.active_pixels = None
         if self.gt_scene:
-            raise NotImplementedError("configs with gt_sdf_dir need the GT mesh tool-chain (trimesh), which is out "
-                                      "of scope; drop dataset.gt_sdf_dir or set Trainer.inv_bounds_transform")
+            self._set_scene_from_config()              # trainer.py:78-81: the oriented scene box feeds the PE transform
+        if self.dataset_format == "realsense_franka_offline":
+            self.set_scene_properties()                # trainer.py:82-83: workspace box from the config
         self.load_networks()
         if chkpt_load_file is not None:
             self.load_checkpoint(chkpt_load_file)
@@ -414,7 +422,14 @@ class Trainer:
         sdf = torch.gather(sdf, 1, order)
         view_depth = render.sdf_render_depth(z, sdf)
         err = torch.abs(view_depth - pts["depth_sample"]) / pts["depth_sample"]
-        prop = (err < self.kf_dist_th).float().mean().item()
+        ok = err < self.kf_dist_th
+        if pts.get("ray_valid") is not None:
+            # fast mode keeps invalid-depth rays in the (fixed-shape) batch; the reference dropped them before the
+            # mean (sample.py:49-55), so they count neither in the numerator nor in the denominator
+            valid = pts["ray_valid"].bool()
+            prop = ((ok & valid).sum().float() / valid.sum().clamp_min(1).float()).item()
+        else:
+            prop = ok.float().mean().item()
         is_kf = prop < self.kf_pixel_ratio
         print("Proportion of loss below threshold", prop, "for KF should be less than", self.kf_pixel_ratio,
               " ---> is keyframe:", is_kf)
@@ -595,7 +610,11 @@ class Trainer:
         if self._xchg_tried or self.dist_world == 1:
             return
         self._xchg_tried = True
-        if self.grad_exchange_mode == "nccl" or self.precision == "fp32":
+        # identical replicas: rank 0's parameters, once, before the first data-parallel step (per-rank torch seeds
+        # -- needed for distinct rays -- would otherwise initialise every replica differently)
+        parallel.broadcast_parameters_(self.sdf_map.flat_parameters())
+        self.sdf_map._packed_sig = None             # the in-place broadcast does not bump the parameters' versions
+        if self.grad_exchange_mode == "nccl" or self.sdf_map.engine().precision == "fp32":
             return
         self._xchg, err = parallel.try_grad_exchange(self.sdf_map.engine(), self.device)
         if self._xchg is None and self.grad_exchange_mode == "multicast":
@@ -651,6 +670,7 @@ class Trainer:
             if g[3] is not None:
                 self._allreduce()
                 g[3].replay()
+            self.optimiser.step_count += 1          # the replay advanced the device-side AdamW counter by one
             if self._xchg is not None:
                 self._xchg.parity = 1 - par
             return g[2]
@@ -707,6 +727,34 @@ class Trainer:
         self.steps_since_frame += 1
         return losses, step_time
 
+    def _set_scene_from_config(self):
+        """Configs with dataset.gt_sdf_dir (replicaCAD.json, scannet.json): the reference loads <gt_sdf_dir>mesh.obj and
+        takes trimesh.bounds.oriented_bounds of it (trainer.py:78-81, 121-123).  Sources, in order: the config entry
+        b200.scene_box = {"T_extent_to_scene": 4x4, "bounds_extents": [3], "scene_center": [3] (optional)}; trimesh, when
+        it is installed and the mesh file exists.  Anything else raises: training without the box would silently fit a
+        different model (the box is the positional encoding's input transform)."""
+        box = self.config.get("b200", {}).get("scene_box")
+        if box is not None:
+            self.set_scene_properties(T_extent_to_scene=np.asarray(box["T_extent_to_scene"], dtype=np.float64),
+                                      bounds_extents=np.asarray(box["bounds_extents"], dtype=np.float64),
+                                      scene_center=None if box.get("scene_center") is None else np.asarray(box["scene_center"]))
+            return
+        try:
+            import trimesh
+        except ImportError:
+            trimesh = None
+        if trimesh is not None and os.path.isfile(self.scene_file):
+            mesh = trimesh.exchange.load.load(self.scene_file, process=False)
+            T, ext = trimesh.bounds.oriented_bounds(mesh)
+            self.set_scene_properties(T_extent_to_scene=T, bounds_extents=ext, scene_center=mesh.bounds.mean(axis=0))
+            return
+        raise NotImplementedError(
+            "config sets dataset.gt_sdf_dir: the reference derives the positional encoding's input transform from the "
+            "oriented bounding box of %s (trimesh.bounds.oriented_bounds).  trimesh is %s; give the box in the config "
+            "as b200.scene_box = {\"T_extent_to_scene\": [[4x4]], \"bounds_extents\": [3]} (the two return values of "
+            "oriented_bounds), or remove dataset.gt_sdf_dir to train without a scene box."
+            % (self.scene_file, "not installed" if trimesh is None else "installed but the mesh file is missing"))
+
     # ---- forward-only inference (row N1 of SURVEY.md 8f) --------------------------------------
     def set_scene_properties(self, scene_mesh=None, T_extent_to_scene=None, bounds_extents=None, scene_center=None):
         """Scene box -> PE transform, grid scale and the grid_dim^3 query points (trainer.py:103-156).
@@ -734,6 +782,9 @@ class Trainer:
         bounds_extents = np.asarray(bounds_extents, dtype=np.float64)
         self.scene_center = scene_center
         self.inv_bounds_transform = torch.from_numpy(T_extent_to_scene).float().to(self.device)
+        if getattr(self, "sdf_map", None) is not None:
+            # called after load_networks: the encoding's transform follows (SDFMap.engine() re-creates its context)
+            self.sdf_map.positional_encoding.transform = self.inv_bounds_transform
         self.bounds_transform_np = np.linalg.inv(T_extent_to_scene)
         self.bounds_transform = torch.from_numpy(self.bounds_transform_np).float().to(self.device)
         grid_range = [-1.0, 1.0]

@@ -17,7 +17,20 @@ import os
 import sys
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("ISDF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """The read-only checkout in the build container; on the GPU box the verbatim copy under oracle/_ref
+    (oracle/make_ref.py).  ISDF_REFERENCE_ROOT overrides both."""
+    env = os.environ.get("ISDF_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", os.path.join(_HERE, "_ref")]:
+        if os.path.isdir(os.path.join(cand, "isdf", "modules")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _ABSENT = {
     "trimesh", "imgviz", "matplotlib", "open3d", "skimage", "pyglet",

@@ -1,5 +1,5 @@
 """Multi-GPU test of the fused gradient exchange (C1 fused into K4): needs >= 2 GPUs on the box, otherwise skipped
-(the single-GPU driver tier).  Spawns tools/test_exchange_2gpu.py under torchrun: the multimem flush must equal the
+(the single-GPU driver tier).  Spawns tools/exchange_check.py under torchrun: the multimem flush must equal the
 NCCL all-reduce of the same per-rank gradients (1e-5), and an eager data-parallel run must follow the same
 trajectory with either exchange."""
 import os
@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_multicast_exchange_matches_nccl():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "test_exchange_2gpu.py")]
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "exchange_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     out = res.stdout + res.stderr
     assert res.returncode == 0, out[-3000:]

@@ -30,7 +30,14 @@ def test_fp32_path_matches_oracle_at_other_shapes(tag, n_freqs, hidden, block):
     out = P.run_train(eng, sd, batch, noise, cfg, DEV)
     ref = P.oracle_train(sd, batch, noise, cfg)
     e = P.compare_train(out, ref)
-    assert e["sdf"] < 5e-6 and e["g"] < 1e-4, e
+    # Bound = 3x the error the reference's OWN fp32 arithmetic makes against fp64 at this shape (the same restatement
+    # evaluated in torch fp32), never tighter than the default-shape bound.  With 11 octaves, sin(2^10 x) in fp32 alone
+    # puts the reference 5.9e-6 away from fp64 (measured: 1.5e-6 / 1.5e-6 / 5.9e-6 for the three shapes), so a fixed
+    # 5e-6 would ask the kernel to beat the arithmetic it is compared with.
+    ref32 = P.oracle_train(sd, batch, noise, cfg, dtype=torch.float32)
+    floor_sdf, floor_g = P.rel(ref32["sdf"], ref["sdf"]), P.rel(ref32["g"], ref["g"])
+    tol_sdf, tol_g = max(5e-6, 3 * floor_sdf), max(1e-4, 3 * floor_g)
+    assert e["sdf"] < tol_sdf and e["g"] < tol_g, (e, floor_sdf, floor_g)
     assert e["total_loss"] < 5e-5 and e["sdf_loss"] < 5e-5, e
     assert e["grad_max_rel_fro"] < 1e-3, e
     # forward-only and forward + input gradient on ragged sizes
@@ -38,7 +45,7 @@ def test_fp32_path_matches_oracle_at_other_shapes(tag, n_freqs, hidden, block):
     layers = [(w.double(), b.double()) for w, b in O.layers_from_state_dict(sd, block)]
     sdf_ref = O.sdf_forward(layers, x.cpu().double(), cfg)
     sdf, g = eng.forward(x, want_grad=True)
-    assert P.rel(sdf.cpu(), sdf_ref) < 5e-6 and P.rel(eng.forward(x).cpu(), sdf_ref) < 5e-6
+    assert P.rel(sdf.cpu(), sdf_ref) < tol_sdf and P.rel(eng.forward(x).cpu(), sdf_ref) < tol_sdf
     assert P.rel(g.cpu(), out["g"].reshape(-1, 3)[:301]) < 1e-4
 
 

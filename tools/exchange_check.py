@@ -1,5 +1,5 @@
 """N-GPU check of the fused gradient exchange (C1 fused into K4) against the NCCL all-reduce.
-   torchrun --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/test_exchange_2gpu.py"""
+   torchrun --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/exchange_check.py"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
