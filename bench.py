@@ -153,7 +153,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--precision", default=os.environ.get("ISDFB_PRECISION", "bf16x3"))
+    ap.add_argument("--precision", default=os.environ.get("ISDFB_PRECISION", "bf16x3g"),
+                    choices=["bf16x3g", "bf16x3", "bf16", "fp32"])
     ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -294,7 +295,8 @@ def main():
         dw_ms = pr["dw_ms"] / max(pr["n_dw"], 1)
         ach = chain_flops / (chain_ms * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops", PEAKS_FALLBACK["bf16_tflops"])
-        roof = {"kernel": "tc_chain_kernel<%d>" % (3 if args.precision == "bf16x3" else 1), "bound": "tensor",
+        roof = {"kernel": {"bf16x3": "tc_chain_kernel<3,1,false>", "bf16x3g": "tc_chain_kernel<3,1,true>",
+                           "bf16": "tc_chain_kernel<1,1,false>"}[args.precision], "bound": "tensor",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peaks["_source"] + " burst bf16", "ms_per_launch": chain_ms,
                 "algorithmic_flops_per_launch": chain_flops, "tiles": tiles,
@@ -328,7 +330,9 @@ def main():
                "iters_per_sec": world * args.steps / (ms_max / 1000.0) / world,
                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": {"bf16x3": "bf16x3 (bf16 hi/lo split, fp32 accumulate)", "bf16": "bf16", "fp32": "f32"}[args.precision],
+               "dtype": {"bf16x3": "bf16x3 (bf16 hi/lo split, fp32 accumulate)",
+                         "bf16x3g": "bf16x3 (bf16 hi/lo split, fp32 accumulate; weight-gradient operands single bf16)",
+                         "bf16": "bf16", "fp32": "f32"}[args.precision],
                "data": "synthetic",
                "config": {"workload": wl["name"], "rays_per_step_per_gpu": rays_per_step, "samples_per_ray": S,
                           "points_per_step_per_gpu": pts_per_step, "keyframes_per_gpu": wl["keyframes"],

@@ -6,4 +6,4 @@ include/isdf_b200.h (isdf_b200/lib/libisdf_b200.so, built by __graft_entry__.bui
 """
 __version__ = "0.1.0"
 
-DEFAULT_PRECISION = "bf16x3"    # overridden by env ISDFB_PRECISION or the config's "b200" section
+DEFAULT_PRECISION = "bf16x3g"    # overridden by env ISDFB_PRECISION or the config's "b200" section

@@ -20,12 +20,16 @@ DEV = torch.device("cuda:0")
 TOL = {
     "fp32": dict(sdf=5e-6, g=1e-4, loss=5e-5, gw=1e-3, gw_small=1e-3),
     "bf16x3": dict(sdf=1e-4, g=1e-3, loss=1e-3, gw=5e-3, gw_small=2e-2),   # north-star: sdf within 1e-4 rel
+    # product default: sdf / g / losses are those of bf16x3 (same products); the weight-gradient operands are single
+    # bf16 (2^-9 relative rounding per operand, unbiased): the measured rel. Frobenius error of dW is ~1.5e-3 at
+    # 27 000 samples -- below the step-to-step sampling noise of the gradient itself (new rays every step)
+    "bf16x3g": dict(sdf=1e-4, g=1e-3, loss=1e-3, gw=5e-3, gw_small=2e-2),
     # fast mode: one bf16 pass.  With Softplus(beta=100) a 2^-9 relative error on a pre-activation of O(1)
     # is comparable to the 0.01-wide transition of the activation, so sigma -- hence d sdf/d x and the
     # gradients -- are only statistically close.  Stated separately; not the parity mode.
     "bf16": dict(sdf=5e-2, g=0.5, loss=0.15, gw=0.5, gw_small=0.6),
 }
-MODES = [m for m in os.environ.get("ISDFB_TEST_MODES", "fp32,bf16x3,bf16").split(",") if m]
+MODES = [m for m in os.environ.get("ISDFB_TEST_MODES", "fp32,bf16x3,bf16x3g,bf16").split(",") if m]
 
 
 def load(name):
@@ -175,7 +179,7 @@ def test_train_properties_full_size(mode):
     b = P.run_train(_engine(cfg, mode, max_points=4096), sd, batch, noise, cfg, DEV)
     # tensor-core modes: a tile's K order is rotated per CTA (tc_chain.cu rot_kstep), so a point that lands on
     # another CTA after re-chunking sees a different fp32 summation order -> equal up to rounding, not bit-wise
-    assert P.rel(a["sdf"], b["sdf"]) < {"fp32": 1e-6, "bf16x3": 5e-5, "bf16": 2e-2}[mode]
+    assert P.rel(a["sdf"], b["sdf"]) < {"fp32": 1e-6, "bf16x3": 5e-5, "bf16x3g": 5e-5, "bf16": 2e-2}[mode]
     assert max(P.rel_fro(x, y) for x, y in zip(a["grads"], b["grads"])) < max(1e-4, 0.1 * t["gw"])
     assert abs(float(a["loss_mat"].double().mean()) - float(a["sums"][3]) / (R * 27)) < 1e-5
     # additivity: grads(first half) + grads(second half) == grads(all) at fixed inv_count

@@ -12,9 +12,9 @@ from tests.golden import trainer_case as TC
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-MODES = [m for m in os.environ.get("ISDFB_TEST_MODES", "fp32,bf16x3,bf16").split(",") if m]
+MODES = [m for m in os.environ.get("ISDFB_TEST_MODES", "fp32,bf16x3,bf16x3g,bf16").split(",") if m]
 # per-step loss tolerance (relative), probe-sdf tolerance (max-abs / max-abs-ref) after 14 AdamW steps
-TOL = {"fp32": (2e-4, 2e-3), "bf16x3": (2e-3, 1e-2), "bf16": (1e-1, 5e-1)}
+TOL = {"fp32": (2e-4, 2e-3), "bf16x3": (2e-3, 1e-2), "bf16x3g": (2e-3, 1e-2), "bf16": (1e-1, 5e-1)}
 
 
 @pytest.fixture(scope="module")
