@@ -120,28 +120,72 @@ def flops_per_point(E, Hd, B, units_only_chain=False):
     return 2 * (6 * f_mac - 2 * E * Hd)
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm overrides it)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return n
+
+
+def make_cpu_stepper(wl, n_keyframes, n_rays=None):
+    """The UNMODIFIED reference Trainer on device 'cpu' (oracle/_ref, or /root/reference in the build container),
+    else the committed port.  -> (stepper, kind, description)"""
+    from oracle import ref_shim
+    cfg = make_config(wl, "fp32", "reference")
+    if ref_shim.available():
+        from oracle.ref_step import RefTrainerStepper
+        st = RefTrainerStepper(cfg, n_keyframes=n_keyframes, n_rays=n_rays)
+        return st, "reference", "unmodified isdf.modules.trainer.Trainer.step() on device 'cpu' (%s)" % st.trainer_file
+    from oracle.cpu_step import CpuStepper
+
+    class _Port:
+        def __init__(self):
+            self.s = CpuStepper(wl["H"], wl["W"], dict(fx=wl["fx"], fy=wl["fy"], cx=wl["cx"], cy=wl["cy"]),
+                                n_frames=5, n_rays=n_rays or wl["n_rays"])
+
+        def step(self):
+            return self.s.step()
+    return _Port(), "port", "oracle/cpu_step.py (torch CPU restatement of the reference step; reference package absent)"
+
+
+def time_cpu(stepper, warmup, steps):
+    for _ in range(warmup):
+        stepper.step()
+    per, pts = [], 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _, n = stepper.step()
+        per.append(time.perf_counter() - t0)
+        pts += n
+    return sum(per), pts, per
+
+
 def run_reference_arm(args, wl, rank):
-    """CPU port of the reference step, all host threads (tier rule: `--impl reference` = CPU path)."""
+    """`--impl reference`: the reference's own CPU implementation of the step on this box's host cores (tier rule),
+    same workload config, metric and unit as the B200 arm.  Rank 0 only; the other ranks exit without work."""
     if rank != 0:
         return
-    from oracle.cpu_step import CpuStepper, time_cpu_steps
-    total = args.steps + args.warmup
-    n_rays = wl["n_rays"]
-    sample = "full workload per step"
-    if total * wl["n_rays"] * 5 * (wl["n_strat"] + wl["n_surf"]) > 16 * 27000:      # keep the run to minutes
-        n_rays = max(8, int(16 * 27000 / (total * 5 * (wl["n_strat"] + wl["n_surf"]))))
-        sample = "%d of %d rays/frame per step (bounded sample)" % (n_rays, wl["n_rays"])
-    st = CpuStepper(wl["H"], wl["W"], dict(fx=wl["fx"], fy=wl["fy"], cx=wl["cx"], cy=wl["cy"]), n_frames=5,
-                    n_rays=n_rays)
-    dt, pts = time_cpu_steps(st, args.warmup, args.steps)
+    cores = host_threads()
+    S = wl["n_strat"] + wl["n_surf"]
+    n_rays, sample = None, "full workload: every step is %d rays x %d samples" % (wl["n_rays"] * 5, S)
+    if wl["n_rays"] * 5 * S > 2 * 27000:         # C4 / C5: a full step is minutes of CPU time -> bounded sample
+        n_rays = max(8, 27000 // (5 * S))
+        sample = "bounded sample: %d of %d rays/frame per step (%d points), same model / loss / window" % (
+            n_rays, wl["n_rays"], n_rays * 5 * S)
+    st, kind, what = make_cpu_stepper(wl, wl["keyframes"], n_rays)
+    dt, pts, per = time_cpu(st, args.warmup, args.steps)
     val = pts / dt
-    cores = torch.get_num_threads()
     out = {"impl": "reference", "metric": "train ray-samples/sec", "value": val, "unit": "ray-samples/s",
            "iters_per_sec": args.steps / dt, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "ms_per_step": 1000.0 * dt / args.steps, "ms_per_step_median": 1000.0 * statistics.median(per),
+           "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": wl["name"], "device": "cpu", "points_per_step": pts // args.steps},
-           "cpu_baseline": {"value": val, "unit": "ray-samples/s", "cores": cores, "kind": "port", "sample": sample},
+           "config": {"workload": wl["name"], "device": "cpu", "points_per_step": pts // args.steps,
+                      "keyframes": wl["keyframes"], "what": what},
+           "cpu_baseline": {"value": val, "unit": "ray-samples/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -255,16 +299,22 @@ def main():
     for i in range(0, args.steps, tr.iters_per_frame):
         _ = tr.scene_dataset[next_frame + (i // tr.iters_per_frame) * world]
     barrier()
+    step_ms, ingest_ms = [], []
     e0.record()
     for i in range(args.steps):
+        t0 = time.perf_counter()
         if i % tr.iters_per_frame == 0:
             fd = tr.get_data([next_frame])
             next_frame += world
             tr.last_is_keyframe = False            # replaces the live (non-key) frame, like add_frame
             tr.add_data(fd)
             h2d += fd.depth_batch_np.nbytes + fd.T_WC_batch_np.nbytes      # fast mode keeps the RGB image on the host
+            t1 = time.perf_counter()
+            ingest_ms.append(1e3 * (t1 - t0))
+            t0 = t1
         losses, _ = tr.step()                      # the reference's call: synchronises and times the step (metrics.py)
         _ = float(losses["total_loss"])            # the step's loss, delivered D2H (pinned) by the step itself
+        step_ms.append(1e3 * (time.perf_counter() - t0))
     e1.record()
     torch.cuda.synchronize(dev)
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -313,17 +363,55 @@ def main():
             roof["hbm_achieved_gbs"] = roof["traffic"] / (chain_ms * 1e-3) / 1e9
             roof["hbm_frac"] = roof["hbm_achieved_gbs"] / hbm_peak
 
-    # ---------------- CPU baseline (oracle port, bounded sample) ----------------
+    # ---------------- data-parallel parity (N > 1): replicas identical, fused exchange == NCCL all-reduce -----------
+    xchg = None
+    used_multicast = tr._xchg is not None
+    if world > 1:
+        flat = tr.sdf_map.flat_parameters()
+        ref0 = flat.clone()
+        dist.broadcast(ref0, 0)
+        dmax = (flat - ref0).abs().max().reshape(1).double()
+        dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+        xchg = {"replica_param_max_abs_diff_vs_rank0": float(dmax.item()), "param_max_abs": float(flat.abs().max().item()),
+                "steps_taken": int(tr.optimiser.step_count)}
+        if tr._xchg is not None and tr._last_pts is not None:
+            # the same per-rank batch (this rank's last sampled rays) through both exchanges: the multimem.red flush
+            # of the weight-gradient kernel, then -- exchange uninstalled -- a plain NCCL all-reduce of the local sums
+            pts, lc = tr._last_pts
+            scratch = torch.zeros(4, dtype=torch.float32, device=dev)
+
+            def k4():
+                eng.train_fwd_bwd(pts["pc"], pts["z_vals"], pts["depth_sample"], pts["dirs_C_sample"], pts["T_WC_sample"],
+                                  pts["norm_sample"], pts["noise"], lc, ray_valid=pts["ray_valid"], want_grad=False,
+                                  loss_sums=scratch)
+            par = tr._xchg.parity
+            eng.select_grad_buffer(par)
+            k4()
+            eng.zero_grad_buffer(1 - par)
+            tr._xchg.barrier()
+            fused = eng.grad_buffer().clone()
+            barrier()
+            tr._xchg.close()
+            eng.zero_grad()
+            k4()
+            summed = eng.grad_buffer().clone()
+            dist.all_reduce(summed)
+            err = ((fused - summed).abs().max() / summed.abs().max()).reshape(1).double()
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+            xchg["fused_vs_nccl_grad_max_rel_diff"] = float(err.item())
+            tr._xchg = None
+        barrier()
+
+    # ---------------- CPU baseline: the reference's own step on this box's host cores (bounded sample) ----------
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        from oracle.cpu_step import CpuStepper, time_cpu_steps
+        cores = host_threads()
         n_r = min(wl["n_rays"], 200)
-        st = CpuStepper(wl["H"], wl["W"], dict(fx=wl["fx"], fy=wl["fy"], cx=wl["cx"], cy=wl["cy"]), n_frames=5,
-                        n_rays=n_r)
-        dt, pts = time_cpu_steps(st, 1, 3)
-        cpu = {"value": pts / dt, "unit": "ray-samples/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "3 steps of %d rays x %d samples after 1 warm-up (oracle/cpu_step.py, torch CPU fp32)" % (n_r * 5, S),
-               "iters_per_sec": 3 / dt}
+        st, kind, what = make_cpu_stepper(wl, 5, n_r)
+        dt, pts, per = time_cpu(st, 1, 5)
+        cpu = {"value": pts / dt, "unit": "ray-samples/s", "cores": cores, "kind": kind,
+               "sample": "5 steps of %d rays x %d samples after 1 warm-up; %s" % (n_r * 5, S, what),
+               "iters_per_sec": 5 / dt, "ms_per_step_median": 1000.0 * statistics.median(per)}
 
     if rank == 0:
         out = {"metric": "train ray-samples/sec", "value": value, "unit": "ray-samples/s",
@@ -339,16 +427,19 @@ def main():
                           "precision": args.precision, "rng_mode": "fast (fixed shapes, validity mask, no host sync; whole step replayed as one CUDA graph)",
                           "parallelism": "dp%d (keyframe-sharded; gradient exchange: %s)" % (world, (
                               "none" if world == 1 else
-                              "fused into the weight-gradient kernel over NVLink multicast (multimem.red) + 1 barrier" if tr._xchg is not None
+                              "fused into the weight-gradient kernel over NVLink multicast (multimem.red) + 1 barrier" if used_multicast
                               else "one NCCL all-reduce of the packed gradient%s" % (" inside the step graph" if tr._nccl_in_graph else ""))),
                           "l2": "no explicit flush: keyframe buffer %.0f MB and per-step side state %.0f MB both exceed the 126 MB L2"
                                 % (wl["keyframes"] * wl["H"] * wl["W"] * 16 / 1e6, pts_per_step * 0.041)},
                "clocks": clocks,
                "e2e": {"value": e2e_val, "unit": "ray-samples/s", "ms_per_step": e2e_ms / args.steps,
+                       "step_ms_median": statistics.median(step_ms),
+                       "ingest_ms_median": statistics.median(ingest_ms) if ingest_ms else None,
+                       "ingest_every_steps": tr.iters_per_frame,
                        "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": 16,
                        "api": "isdf.modules.trainer.Trainer.get_data/add_data/step() + float(losses['total_loss'])"},
                "gpu_launches": launches,
-               "roofline": roof, "cpu_baseline": cpu}
+               "roofline": roof, "cpu_baseline": cpu, "exchange_parity": xchg}
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -123,6 +123,30 @@ int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC /*[F,4,4]*/, const int64
                       float* pc /*[R,S,3]*/, float* z_vals /*[R,S]*/, float* dirs_C /*[R,3]*/,
                       float* T_WC_sample /*[R,4,4]*/, void* stream);
 
+/* ---- K1 fused (fast mode): one launch for sample_pixels + get_batch_data + sample_along_rays + noise -------------
+ * sample.py:11-21 (uniform pixels, n_rays_per_frame per window slot), :24-74 (gather; a validity mask replaces the
+ * data-dependent compaction), :131-178 + transform.py:36-41 (depths along rays, world points) and the N(0,1) output
+ * noise of SDFMap.forward (fc_map.py:106-108).  Random numbers come from Philox4x32-10 inside the kernel, keyed by
+ * (seed, ray, sample) and advanced by a per-ctx DEVICE step counter, so a CUDA-graph replay draws fresh numbers;
+ * the distributions are the reference's, the number stream is not torch's (use the separate K1 entries with
+ * torch-drawn numbers to replay a reference run).  inv_count[0] = 1 / max(#valid rays * S, 1) for the loss mean.
+ * norm_sample may be NULL iff normals is NULL; noise may be NULL.                                             */
+int isdfb_sample_fused(isdfb_ctx* ctx, const float* depth, const float* normals, const float* T_WC,
+                       const int64_t* frame_map, int32_t normals_use_frame_map, int32_t n_frames,
+                       int32_t n_rays_per_frame, int32_t n_strat, int32_t n_surf, const isdfb_camera* cam,
+                       float min_depth, float dist_behind, const float* lin, uint64_t seed, int64_t* ib, int64_t* ih,
+                       int64_t* iw, float* pc, float* z_vals, float* dirs_C, float* T_WC_sample, float* depth_sample,
+                       float* norm_sample, uint8_t* ray_valid, float* noise, float* inv_count, void* stream);
+
+/* ---- A0 (fast mode): the keyframe window on the device ---------------------------------------------------------
+ * trainer.py:652-674 select_keyframes: frame_map[0 .. window_size-3] = (window_size - 2) of the keyframes
+ * 0 .. n_frames-3 drawn WITHOUT replacement with p ~ frame_avg_losses (np.random.choice(..., replace=False, p=...));
+ * frame_map[window_size-2 ..] = the two latest.  Gumbel top-k with Philox numbers keyed by (seed, frame) and the
+ * same device step counter as isdfb_sample_fused (which advances it), so a graph replay draws a fresh window.
+ * All-zero losses -> uniform draw.  Requires n_frames > window_size >= 2.                                      */
+int isdfb_select_window(isdfb_ctx* ctx, const float* frame_avg_losses /*[n_frames]*/, int32_t n_frames,
+                        int32_t window_size, uint64_t seed, int64_t* frame_map /*[window_size]*/, void* stream);
+
 /* ---- N3: frame ingest (row "next" of SURVEY.md 8f) -------------------------------------------
  * Per-pixel normals of one depth image [H,W] -> normals [H,W,3]; fuses
  * transform.pointcloud_from_depth_torch + estimate_pointcloud_normals (transform.py:169-196, 215-270;
@@ -182,6 +206,18 @@ int isdfb_frame_bins(isdfb_ctx* ctx, const float* loss_mat, const uint8_t* ray_v
                      const int64_t* ib, const int64_t* ih, const int64_t* iw, int64_t n_rays,
                      int32_t n_samples, int32_t n_frames, int32_t H, int32_t W, int32_t factor,
                      float* loss_approx, float* frame_avg, void* stream);
+
+/* K5 + the step's bookkeeping in the same launches (the graphed fast-mode step): as isdfb_frame_bins, plus
+ *   frame_avg_losses[frame_map[f]] = frame_avg[f]      -- trainer.py:979 `frames.frame_avg_losses[idxs] = ...`
+ *   means_out[i] = loss_sums[i] * inv_count[0], i < 4  -- the loss means the reference reads with .item()
+ *                                                          (loss.py:187-203); loss_sums is then CLEARED, so the next
+ *                                                          isdfb_train_fwd_bwd accumulates from zero.
+ * frame_map NULL = identity; frame_avg_losses / means_out NULL = skip that part.                              */
+int isdfb_step_finish(isdfb_ctx* ctx, const float* loss_mat, const uint8_t* ray_valid,
+                      const int64_t* ib, const int64_t* ih, const int64_t* iw, int64_t n_rays,
+                      int32_t n_samples, int32_t n_frames, int32_t H, int32_t W, int32_t factor,
+                      float* loss_approx, float* frame_avg, const int64_t* frame_map, float* frame_avg_losses,
+                      float* loss_sums, const float* inv_count, float* means_out, void* stream);
 
 /* ---- K6: AdamW + weight re-pack --------------------------------------------------------
  * torch.optim.AdamW.step for the flat parameter vector (trainer.py:435-439, 982) using the

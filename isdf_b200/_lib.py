@@ -49,6 +49,8 @@ SIGNATURES = {
     "isdfb_gather_rays": (C.c_int, [P, P, P, P, I32, P, P, P, I64, C.POINTER(Camera), P, P, P, P]),
     "isdfb_sample_rays": (C.c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I32, I32, C.POINTER(Camera), F, F,
                                     P, P, P, P, P]),
+    "isdfb_sample_fused": (C.c_int, [P, P, P, P, P, I32, I32, I32, I32, I32, C.POINTER(Camera), F, F, P, C.c_uint64,
+                                     P, P, P, P, P, P, P, P, P, P, P, P, P]),
     "isdfb_ingest_normals": (C.c_int, [P, P, C.POINTER(Camera), P, P]),
     "isdfb_pe_encode": (C.c_int, [P, P, I64, P, P]),
     "isdfb_mlp_forward": (C.c_int, [P, P, P, F, I64, P, P]),
@@ -61,6 +63,8 @@ SIGNATURES = {
     "isdfb_zero_grad_buffer": (C.c_int, [P, I32, P]),
     "isdfb_export_grads": (C.c_int, [P, P, P]),
     "isdfb_frame_bins": (C.c_int, [P, P, P, P, P, P, I64, I32, I32, I32, I32, I32, P, P, P]),
+    "isdfb_step_finish": (C.c_int, [P, P, P, P, P, P, I64, I32, I32, I32, I32, I32, P, P, P, P, P, P, P, P]),
+    "isdfb_select_window": (C.c_int, [P, P, I32, I32, C.c_uint64, P, P]),
     "isdfb_adamw": (C.c_int, [P, P, P, P, I64, F, F, F, F, F, F, P]),
     "isdfb_adamw_graph": (C.c_int, [P, P, P, P, F, F, F, F, F, F, P]),
     "isdfb_adamw_set_step": (C.c_int, [P, I64, P]),

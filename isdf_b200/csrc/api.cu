@@ -10,8 +10,13 @@ int sample_along(isdfb_ctx*, const float*, const int64_t*, const int64_t*, const
                  const float*, const float*, const float*, const float*, const float*, const float*, const float*, int64_t,
                  int, int, const isdfb_camera*, float, float, float*, float*, float*, float*, cudaStream_t);
 int sample_frame_bins(isdfb_ctx*, float*, const float*, const uint8_t*, const int64_t*, const int64_t*,
-                      const int64_t*, int64_t, int, int, int, int, int, float*, float*, cudaStream_t);
+                      const int64_t*, int64_t, int, int, int, int, int, float*, float*, const int64_t*, float*, float*,
+                      const float*, float*, cudaStream_t);
+int sample_select_window(isdfb_ctx*, void*, const float*, int, int, uint64_t, int64_t*, cudaStream_t);
 int sample_ingest_normals(isdfb_ctx*, const float*, const isdfb_camera*, float*, cudaStream_t);
+int sample_fused(isdfb_ctx*, void*, const float*, const float*, const float*, const int64_t*, int, int, int, int, int,
+                 const isdfb_camera*, float, float, const float*, uint64_t, int64_t*, int64_t*, int64_t*, float*, float*,
+                 float*, float*, float*, float*, uint8_t*, float*, float*, cudaStream_t);
 int bounds_pc_launch(isdfb_ctx*, const float*, const float*, const float*, const uint8_t*, int64_t, int32_t, float*,
                      float*, cudaStream_t);
 int tc_create(isdfb_ctx* ctx);
@@ -98,6 +103,8 @@ int isdfb_create(const isdfb_model_cfg* cfg, int device, isdfb_ctx** out) {
   CREATE_CUDA(cudaMemset(ctx->g_packed, 0, ctx->lay.n_packed * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&ctx->adam_dev, 64));
   CREATE_CUDA(cudaMemset(ctx->adam_dev, 0, 64));
+  CREATE_CUDA(cudaMalloc(&ctx->sample_dev, 64));
+  CREATE_CUDA(cudaMemset(ctx->sample_dev, 0, 64));
   if (cfg->precision == ISDFB_PREC_FP32) {
     simt_workspace_floats(ctx->lay, ctx->cap, &ctx->ws_floats);
   } else {
@@ -121,6 +128,7 @@ int isdfb_destroy(isdfb_ctx* ctx) {
   if (ctx->g_own) cudaFree(ctx->g_own);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->adam_dev) cudaFree(ctx->adam_dev);
+  if (ctx->sample_dev) cudaFree(ctx->sample_dev);
   delete ctx;
   return ISDFB_OK;
 }
@@ -168,6 +176,23 @@ int isdfb_sample_rays(isdfb_ctx* ctx, const float* T_WC, const int64_t* frame_ma
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_rays: bad sample counts (n_strat %d n_surf %d)", n_strat, n_surf);
   return sample_along(ctx, T_WC, frame_map, ib, ih, iw, dirs_C_in, depth_sample, far, near, u_strat, n_near, lin, n_rays, n_strat,
                       n_surf, cam, min_depth, dist_behind, pc, z_vals, dirs_C, T_WC_sample, st);
+}
+
+int isdfb_sample_fused(isdfb_ctx* ctx, const float* depth, const float* normals, const float* T_WC,
+                       const int64_t* frame_map, int32_t normals_use_frame_map, int32_t n_frames,
+                       int32_t n_rays_per_frame, int32_t n_strat, int32_t n_surf, const isdfb_camera* cam,
+                       float min_depth, float dist_behind, const float* lin, uint64_t seed, int64_t* ib, int64_t* ih,
+                       int64_t* iw, float* pc, float* z_vals, float* dirs_C, float* T_WC_sample, float* depth_sample,
+                       float* norm_sample, uint8_t* ray_valid, float* noise, float* inv_count, void* stream) {
+  ENTER(ctx);
+  if (n_frames <= 0 || n_rays_per_frame <= 0) return ISDFB_OK;
+  if (!depth || !T_WC || !cam || !lin || !ib || !ih || !iw || !pc || !z_vals || !dirs_C || !T_WC_sample || !depth_sample ||
+      !ray_valid || !inv_count || (normals && !norm_sample))
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_fused: null argument");
+  if (n_strat < 1 || n_surf < 1) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_sample_fused: bad sample counts (n_strat %d n_surf %d)", n_strat, n_surf);
+  return sample_fused(ctx, ctx->sample_dev, depth, normals, T_WC, frame_map, normals_use_frame_map, n_frames, n_rays_per_frame,
+                      n_strat, n_surf, cam, min_depth, dist_behind, lin, seed, ib, ih, iw, pc, z_vals, dirs_C, T_WC_sample,
+                      depth_sample, norm_sample, ray_valid, noise, inv_count, st);
 }
 
 int isdfb_ingest_normals(isdfb_ctx* ctx, const float* depth, const isdfb_camera* cam, float* normals, void* stream) {
@@ -306,7 +331,36 @@ int isdfb_frame_bins(isdfb_ctx* ctx, const float* loss_mat, const uint8_t* ray_v
   if ((int64_t)n_frames * factor * factor * 2 > 65536)
     ISDFB_FAIL(ctx, ISDFB_ERR_CAPACITY, "too many frames (%d) for the histogram scratch", n_frames);
   return sample_frame_bins(ctx, g_scratch_of(ctx), loss_mat, ray_valid, ib, ih, iw, n_rays, n_samples, n_frames,
-                           H, W, factor, loss_approx, frame_avg, st);
+                           H, W, factor, loss_approx, frame_avg, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+}
+
+int isdfb_step_finish(isdfb_ctx* ctx, const float* loss_mat, const uint8_t* ray_valid, const int64_t* ib,
+                      const int64_t* ih, const int64_t* iw, int64_t n_rays, int32_t n_samples, int32_t n_frames,
+                      int32_t H, int32_t W, int32_t factor, float* loss_approx, float* frame_avg,
+                      const int64_t* frame_map, float* frame_avg_losses, float* loss_sums, const float* inv_count,
+                      float* means_out, void* stream) {
+  ENTER(ctx);
+  if (!loss_approx || !frame_avg || (n_rays > 0 && (!loss_mat || !ib || !ih || !iw)))
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_step_finish: null argument");
+  if (means_out && (!loss_sums || !inv_count))
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_step_finish: means_out needs loss_sums and inv_count");
+  if (factor < 1 || H % factor || W % factor)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "H (%d) and W (%d) must be divisible by factor %d (loss.py:209-211)", H, W, factor);
+  if (n_frames < 1 || (int64_t)n_frames * factor * factor * 2 > 65536)
+    ISDFB_FAIL(ctx, ISDFB_ERR_CAPACITY, "bad number of frames (%d) for the histogram scratch", n_frames);
+  return sample_frame_bins(ctx, g_scratch_of(ctx), loss_mat, ray_valid, ib, ih, iw, n_rays, n_samples, n_frames,
+                           H, W, factor, loss_approx, frame_avg, frame_map, frame_avg_losses, loss_sums, inv_count,
+                           means_out, st);
+}
+
+int isdfb_select_window(isdfb_ctx* ctx, const float* frame_avg_losses, int32_t n_frames, int32_t window_size,
+                        uint64_t seed, int64_t* frame_map, void* stream) {
+  ENTER(ctx);
+  if (!frame_avg_losses || !frame_map) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_select_window: null argument");
+  if (window_size < 2 || window_size > 66 || n_frames <= window_size)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_select_window: needs 2 <= window_size (%d) <= 66 and n_frames (%d) > window_size",
+               window_size, n_frames);
+  return sample_select_window(ctx, ctx->sample_dev, frame_avg_losses, n_frames, window_size, seed, frame_map, st);
 }
 
 int isdfb_adamw(isdfb_ctx* ctx, float* params_flat, float* m, float* v, int64_t step, float lr, float beta1,

@@ -66,6 +66,7 @@ struct isdfb_ctx {
   // tensor-core path workspace -- see tc_chain.cu
   void* tc;                // opaque
   void* adam_dev;          // device AdamDev {step_size, bc2_sqrt, step} for the graph-safe K6
+  void* sample_dev;        // device FusedSampleState {step, valid, blocks_done} of the fused fast-mode sampler
 };
 
 extern char g_isdfb_create_err[512];

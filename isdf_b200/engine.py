@@ -138,6 +138,34 @@ class Engine:
                                             self._stream()))
         return pc, z, dirs_C, T_s
 
+    def sample_fused(self, depth, normals, T_WC, frame_map, n_frames, n_rays, n_strat, n_surf, cam, min_depth,
+                     dist_behind, lin, seed, want_noise=True, normals_use_frame_map=False):
+        """K1 fused (fast mode): pixels, gather, depths along rays, world points and the output noise in one
+        launch with in-kernel Philox numbers.  Returns the sample dict fields."""
+        dev = self.device
+        depth, T_WC = _f32(depth, "depth", dev), _f32(T_WC, "T_WC", dev)
+        normals = _f32(normals, "normals", dev)
+        frame_map = _i64(frame_map, "frame_map", dev)
+        lin = _f32(lin, "lin", dev)
+        R, S = int(n_frames) * int(n_rays), int(n_strat) + int(n_surf)
+        i64 = dict(dtype=torch.int64, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        ib, ih, iw = torch.empty(R, **i64), torch.empty(R, **i64), torch.empty(R, **i64)
+        pc, z = torch.empty(R, S, 3, **f32), torch.empty(R, S, **f32)
+        dirs_C, T_s, d_s = torch.empty(R, 3, **f32), torch.empty(R, 4, 4, **f32), torch.empty(R, **f32)
+        n_s = torch.empty(R, 3, **f32) if normals is not None else None
+        valid = torch.empty(R, dtype=torch.uint8, device=dev)
+        noise = torch.empty(R, S, **f32) if want_noise else None
+        inv = torch.empty(1, **f32)
+        self._ck(self.lib.isdfb_sample_fused(self._ctx, _ptr(depth), _ptr(normals), _ptr(T_WC), _ptr(frame_map),
+                                             1 if normals_use_frame_map else 0, int(n_frames), int(n_rays), int(n_strat),
+                                             int(n_surf), C.byref(cam), float(min_depth), float(dist_behind), _ptr(lin),
+                                             C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(ib), _ptr(ih), _ptr(iw), _ptr(pc),
+                                             _ptr(z), _ptr(dirs_C), _ptr(T_s), _ptr(d_s), _ptr(n_s), _ptr(valid), _ptr(noise),
+                                             _ptr(inv), self._stream()))
+        return dict(pc=pc, z_vals=z, indices_b=ib, indices_h=ih, indices_w=iw, dirs_C_sample=dirs_C, depth_sample=d_s,
+                    T_WC_sample=T_s, norm_sample=n_s, ray_valid=valid, noise=noise, inv_count_dev=inv)
+
     def ingest_normals(self, depth, cam):
         depth = _f32(depth, "depth", self.device)
         out = torch.empty(*depth.shape, 3, dtype=torch.float32, device=self.device)
@@ -253,6 +281,34 @@ class Engine:
                                            R, S, int(n_frames), int(H), int(W), int(factor), _ptr(approx),
                                            _ptr(favg), self._stream()))
         return approx, favg
+
+    def step_finish(self, loss_mat, ib, ih, iw, n_frames, H, W, factor, ray_valid, frame_map, frame_avg_losses,
+                    loss_sums, inv_count, means_out):
+        """K5 + write-back of the per-keyframe losses + the four loss means (clears loss_sums); see the header."""
+        dev = self.device
+        R, S = loss_mat.shape
+        approx = torch.empty(n_frames, factor, factor, dtype=torch.float32, device=dev)
+        favg = torch.empty(n_frames, dtype=torch.float32, device=dev)
+        for t, nm in ((frame_avg_losses, "frame_avg_losses"), (loss_sums, "loss_sums"), (inv_count, "inv_count"),
+                      (means_out, "means_out")):
+            if t is not None and (t.dtype != torch.float32 or t.device != dev or not t.is_contiguous()):
+                raise TypeError("%s must be a contiguous float32 tensor on %s" % (nm, dev))
+        if ray_valid is not None:
+            ray_valid = ray_valid.to(torch.uint8).contiguous()
+        self._ck(self.lib.isdfb_step_finish(self._ctx, _ptr(loss_mat), _ptr(ray_valid), _ptr(ib), _ptr(ih), _ptr(iw), R, S,
+                                            int(n_frames), int(H), int(W), int(factor), _ptr(approx), _ptr(favg),
+                                            _ptr(frame_map), _ptr(frame_avg_losses), _ptr(loss_sums), _ptr(inv_count),
+                                            _ptr(means_out), self._stream()))
+        return approx, favg
+
+    def select_window(self, frame_avg_losses, n_frames, window_size, seed, out=None):
+        """A0 on the device: Gumbel top-k window (see isdfb_select_window)."""
+        w = _f32(frame_avg_losses, "frame_avg_losses", self.device)
+        if out is None:
+            out = torch.empty(window_size, dtype=torch.int64, device=self.device)
+        self._ck(self.lib.isdfb_select_window(self._ctx, _ptr(w), int(n_frames), int(window_size),
+                                              C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(out), self._stream()))
+        return out
 
     # ---- K6 ----------------------------------------------------------
     def adamw(self, params, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):

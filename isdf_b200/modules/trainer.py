@@ -139,6 +139,9 @@ class Trainer:
         self.fix_normal_window = bool(b200.get("fix_normal_window", 0))
         self.max_points = int(b200.get("max_points", 32768))
         self.use_graph = bool(b200.get("cuda_graph", 1))
+        # fast mode: K1 fused sampler with in-kernel Philox numbers (one launch instead of ~10 torch kernels)
+        self.fused_sampler = bool(b200.get("fused_sampler", int(os.environ.get("ISDFB_FUSED_SAMPLER", "1"))))
+        self._sampler_seed = None
         self._graph = None
         self._graph_seen = None
         self._plist = None
@@ -170,6 +173,10 @@ class Trainer:
         self.sdf_map.train()
         self.cosSim = torch.nn.CosineSimilarity(dim=-1, eps=1e-6)
         self._loss_sums = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._loss_sums_fused = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._means_dev = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._arange_cache = {}
+        self._last_pts = None
         self._lin_cache = {}
 
     def __getattr__(self, name):
@@ -484,6 +491,15 @@ class Trainer:
         eng = self.sdf_map.engine()
         dev = self.device
         n_frames = depth_batch.shape[0] if frame_map is None else len(frame_map)
+        if self.rng_mode == "fast" and self.fused_sampler and n_surf >= 1 and self.rng_device is None:
+            if self._sampler_seed is None:            # one draw from torch's generator seeds the in-kernel stream
+                self._sampler_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            fmap = None if frame_map is None else torch.as_tensor(frame_map, device=dev, dtype=torch.int64)
+            out = eng.sample_fused(depth_batch, norm_batch, T_WC_batch, fmap, n_frames, n_rays, n_strat, n_surf,
+                                   self.cam, self.min_depth, dist_behind_surf, self._lin(n_strat), self._sampler_seed,
+                                   want_noise=True, normals_use_frame_map=self.fix_normal_window)
+            out.update(depth_batch=depth_batch, binary_masks=None, n_frames=n_frames)
+            return out
         rd = self.rng_device or dev
         ib, ih, iw = sample.sample_pixels(n_rays, n_frames, self.H, self.W, device=rd)
         ib, ih, iw = ib.to(dev), ih.to(dev), iw.to(dev)
@@ -528,9 +544,13 @@ class Trainer:
                                               ray_valid=ray_valid)
         noise = None
         if self.noise_std is not None:
-            noise = torch.randn(R, S, device=self.rng_device or self.device).to(self.device)
-        inv_dev = None
-        if ray_valid is None:
+            noise = sample_pts.get("noise")           # drawn by the fused sampler, else here (fc_map.py:106-108)
+            if noise is None:
+                noise = torch.randn(R, S, device=self.rng_device or self.device).to(self.device)
+        inv_dev = sample_pts.get("inv_count_dev")     # 1 / (valid rays * S), computed by the fused sampler
+        if inv_dev is not None:
+            inv_count = 0.0
+        elif ray_valid is None:
             inv_count = 1.0 / max(R * S, 1)
         else:
             inv_count = 0.0
@@ -580,8 +600,71 @@ class Trainer:
         return total_loss, losses, loss_approx, frame_avg_loss
 
     # ---- one optimisation step (trainer.py:951-1016) -----------------------------------------
+    def _fused_front_ok(self):
+        return (self.rng_mode == "fast" and self.fused_sampler and self.rng_device is None and self.n_surf_samples >= 1
+                and self.window_size <= 66)
+
+    def _step_front_fused(self, zero_grad=True):
+        """fast mode, all on the device and all in this library's kernels: window (A0, Gumbel top-k) -> fused sampler
+        (A1-A3 + the noise draw) -> [bounds 'pc'] -> K4 -> K5 + write-back of the per-keyframe losses + loss means.
+        No torch kernel is launched; the only torch node of a captured step is the 16-byte D2H copy of the means."""
+        eng = self.sdf_map.engine()
+        f = self.frames
+        n = len(f)
+        dev = self.device
+        if self._sampler_seed is None:            # one draw from torch's generator seeds the in-kernel streams
+            self._sampler_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if n > self.window_size and self.incremental:
+            fmap = eng.select_window(f.frame_avg_losses, n, self.window_size, self._sampler_seed)
+        else:
+            fmap = self._arange_cache.get(n)
+            if fmap is None:
+                fmap = self._arange_cache[n] = torch.arange(n, device=dev, dtype=torch.int64)
+        self.active_idxs = fmap
+        n_win = int(fmap.shape[0])
+        norm_batch = f.normal_batch if self.do_normal else None
+        pts = eng.sample_fused(f.depth_batch, norm_batch, f.T_WC_batch, fmap, n_win, self.n_rays,
+                               self.n_strat_samples, self.n_surf_samples, self.cam, self.min_depth,
+                               self.dist_behind_surf, self._lin(self.n_strat_samples), self._sampler_seed,
+                               want_noise=self.noise_std is not None, normals_use_frame_map=self.fix_normal_window)
+        self.active_pixels = {k: pts[k] for k in ("indices_b", "indices_h", "indices_w")}
+        if self.bounds_method == "normal":
+            raise TypeError("bounds_method 'normal' is broken in the reference itself (loss.py:29) and is not supported")
+        pc_bounds = pc_vec = None
+        if self.bounds_method == "pc":
+            pc_bounds, pc_vec = eng.bounds_pc(pts["pc"], pts["z_vals"], pts["depth_sample"], ray_valid=pts["ray_valid"])
+        inv_dev = pts["inv_count_dev"]
+        lc = make_loss_cfg(self.trunc_weight, self.trunc_distance, self.eik_weight, self.eik_apply_dist,
+                           self.grad_weight, self.orien_loss, self.loss_type, self.noise_std or 0.0, 0.0,
+                           inv_count_dev=inv_dev, bounds=pc_bounds, grad_vec=pc_vec)
+        if zero_grad:
+            eng.zero_grad()
+        # loss_sums is cleared by the previous step's isdfb_step_finish (and at allocation)
+        sdf, _, loss_mat, _ = eng.train_fwd_bwd(pts["pc"], pts["z_vals"], pts["depth_sample"], pts["dirs_C_sample"],
+                                                pts["T_WC_sample"], pts["norm_sample"] if self.do_normal else None,
+                                                pts["noise"], lc, ray_valid=pts["ray_valid"], want_grad=False,
+                                                loss_sums=self._loss_sums_fused)
+        self.last_sdf, self.last_loss_mat = sdf, loss_mat
+        self._last_pts = (pts, lc)            # the step's batch (kept for diagnostics: bench.py re-runs K4 on it)
+        eng.step_finish(loss_mat, pts["indices_b"], pts["indices_h"], pts["indices_w"], n_win, self.H, self.W,
+                        self.loss_approx_factor, pts["ray_valid"], fmap, f.frame_avg_losses, self._loss_sums_fused,
+                        inv_dev, self._means_dev)
+        if self._loss_host is None:
+            self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self._loss_host.copy_(self._means_dev, non_blocking=True)
+        host = self._loss_host
+        losses = {"sdf_loss": host[0]}
+        if self.grad_weight != 0:
+            losses["grad_loss"] = host[1]
+        if self.eik_weight != 0:
+            losses["eikonal_loss"] = host[2]
+        losses["total_loss"] = host[3]
+        return losses
+
     def _step_front(self, zero_grad=True):
         """Everything up to and including the fused forward/backward (gradient left in the engine)."""
+        if self._fused_front_ok():
+            return self._step_front_fused(zero_grad=zero_grad)
         depth_batch = self.frames.depth_batch
         T_WC_batch = self.frames.T_WC_batch
         norm_batch = self.frames.normal_batch if self.do_normal else None

@@ -75,7 +75,7 @@ class RefTrainerStepper:
     def step(self):
         with contextlib.redirect_stdout(io.StringIO()):
             losses, _ = self.tr.step()
-        return float(losses["total_loss"]), self.points_per_step
+        return float(losses["total_loss"].detach()), self.points_per_step
 
 
 def time_steps(stepper, warmup, steps):

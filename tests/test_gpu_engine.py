@@ -121,6 +121,61 @@ def test_forward_ragged_sizes_and_noise(mode):
     assert eng.forward(torch.empty(0, 3, device=DEV)).numel() == 0
 
 
+def test_fused_sampler_matches_the_separate_kernels_in_distribution():
+    """K1 fused (fast mode): same geometry as gather_rays + sample_rays on the pixels it drew, the reference's
+    distributions for every random quantity, fresh numbers on every call and on every CUDA-graph replay."""
+    from isdf_b200.engine import make_camera
+    F, H, W, n_rays, n_strat, n_surf = 4, 96, 128, 512, 19, 8
+    S = n_strat + n_surf
+    depth = torch.stack([C.synthetic_depth(k, H, W, invalid_frac=0.1) for k in range(F + 2)]).to(DEV)
+    nrm = torch.stack([C.synthetic_normals(H, W, 0.05, 70 + k) for k in range(F + 2)]).to(DEV)
+    T = torch.stack([C.synthetic_pose(k) for k in range(F + 2)]).to(DEV)
+    fmap = torch.tensor([5, 0, 3, 2], device=DEV)
+    cam = make_camera(100.0, 101.0, 63.5, 47.5, H, W)
+    lin = torch.linspace(0, 1, n_strat + 1).to(DEV)
+    eng = _engine(O.default_cfg(), "fp32", max_points=1024)
+    a = eng.sample_fused(depth, nrm, T, fmap, F, n_rays, n_strat, n_surf, cam, 0.07, 0.1, lin, seed=1234)
+    R = F * n_rays
+    ib, ih, iw = a["indices_b"], a["indices_h"], a["indices_w"]
+    assert torch.equal(ib, torch.arange(F, device=DEV).repeat_interleave(n_rays))
+    assert int(ih.min()) >= 0 and int(ih.max()) < H and int(iw.min()) >= 0 and int(iw.max()) < W
+    assert abs(float(ih.float().mean()) - (H - 1) / 2) < 0.05 * H and abs(float(iw.float().mean()) - (W - 1) / 2) < 0.05 * W
+    # gather + geometry: the separate K1 kernels on the same pixels / numbers give the same values
+    d2, n2, v2 = eng.gather_rays(depth, nrm, ib, ih, iw, cam, frame_map=fmap)
+    assert torch.equal(d2, a["depth_sample"]) and torch.equal(v2, a["ray_valid"])
+    assert torch.equal(torch.nan_to_num(n2, nan=7.0), torch.nan_to_num(a["norm_sample"], nan=7.0))
+    z, d = a["z_vals"], a["depth_sample"]
+    far = d + 0.1
+    u = ((z[:, n_surf:] - 0.07) / (far - 0.07)[:, None] * n_strat - torch.arange(n_strat, device=DEV)[None, :])
+    ok = a["ray_valid"].bool()
+    assert torch.equal(z[:, 0], d)
+    assert float(u[ok].min()) > -1e-4 and float(u[ok].max()) < 1 + 1e-4 and abs(float(u[ok].mean()) - 0.5) < 0.02
+    near = z[:, 1:n_surf]
+    assert bool((near[ok] >= 0.07).all()) and bool((near[ok] <= far[ok][:, None] + 1e-6).all())
+    inner = (near > 0.07 + 1e-6) & (near < far[:, None] - 1e-6) & ok[:, None]
+    off = (near - d[:, None])[inner]                      # un-clamped offsets ~ N(0, 0.1^2) truncated at +0.1
+    assert abs(float(off[off < 0].std()) / 0.1 - 0.6028) < 0.05          # std of a half-normal = 0.6028 sigma
+    nz = a["noise"]
+    assert abs(float(nz.mean())) < 0.02 and abs(float(nz.std()) - 1.0) < 0.02
+    dirs = a["dirs_C_sample"]
+    assert torch.allclose(dirs[:, 0], (iw.float() - 63.5) / 100.0) and torch.allclose(dirs[:, 1], (ih.float() - 47.5) / 101.0)
+    Ts = T[fmap[ib]]
+    assert torch.equal(a["T_WC_sample"], Ts)
+    pc_ref = Ts[:, None, :3, 3] + (Ts[:, :3, :3] @ dirs[:, :, None])[:, None, :, 0] * z[:, :, None]
+    assert torch.allclose(a["pc"], pc_ref, atol=1e-5)
+    assert abs(float(a["inv_count_dev"]) - 1.0 / (int(ok.sum()) * S)) < 1e-9
+    # fresh numbers per call, and per graph replay (the step counter lives on the device)
+    b = eng.sample_fused(depth, nrm, T, fmap, F, n_rays, n_strat, n_surf, cam, 0.07, 0.1, lin, seed=1234)
+    assert not torch.equal(a["indices_h"], b["indices_h"]) and not torch.equal(a["noise"], b["noise"])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        c = eng.sample_fused(depth, nrm, T, fmap, F, n_rays, n_strat, n_surf, cam, 0.07, 0.1, lin, seed=1234)
+    g.replay(); torch.cuda.synchronize(); h1 = c["indices_h"].clone()
+    g.replay(); torch.cuda.synchronize()
+    assert not torch.equal(h1, c["indices_h"])
+
+
 # ---------------------------------------------------------------------------------- K4
 CASES = [("c1", 31, 1.0, None, 48, 0.25, "L1"),
          ("c2_rigid_gain2", 32, 2.0, 9, 40, 0.04, "L1"),
