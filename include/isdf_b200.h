@@ -168,6 +168,15 @@ int isdfb_mlp_forward(isdfb_ctx* ctx, const float* x, const float* noise, float 
 int isdfb_mlp_forward_grad(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std,
                            int64_t n, float* sdf, float* grad, void* stream);
 
+/* K2 over the lattice of Trainer.get_sdf_grid (trainer.py:1426-1444; points = geometry.transform.make_3D_grid,
+ * transform.py:273-304): sdf[(i*dim + j)*dim + k] for x = T (lin[i] s_x, lin[j] s_y, lin[k] s_z), generated inside
+ * the kernel -- the [dim^3, 3] point array (96 MB at dim 200) is never read or written.  lin = torch.linspace(lo, hi,
+ * dim) on the device (passed in so that the abscissae are torch's); scale [3] and transform [3x4 row-major] are HOST
+ * arrays, either may be NULL.                                                                                    */
+int isdfb_mlp_forward_grid(isdfb_ctx* ctx, const float* lin /*[dim], device*/, int32_t dim,
+                           const float* scale /*[3], host*/, const float* transform /*[12], host*/,
+                           float* sdf /*[dim^3], device*/, void* stream);
+
 /* ---- N2: batch-distance bound ("pc", row "next" of SURVEY.md 8f) -------------------------------
  * loss.bounds_pc (loss.py:56-89): for every sample, the distance to the closest SURFACE sample of the
  * batch (pc[r,0,:] of every valid ray), negated where z > depth, and the unit vector from that surface

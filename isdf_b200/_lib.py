@@ -55,6 +55,7 @@ SIGNATURES = {
     "isdfb_pe_encode": (C.c_int, [P, P, I64, P, P]),
     "isdfb_mlp_forward": (C.c_int, [P, P, P, F, I64, P, P]),
     "isdfb_mlp_forward_grad": (C.c_int, [P, P, P, F, I64, P, P, P]),
+    "isdfb_mlp_forward_grid": (C.c_int, [P, P, I32, C.POINTER(F), C.POINTER(F), P, P]),
     "isdfb_bounds_pc": (C.c_int, [P, P, P, P, P, I64, I32, P, P, P]),
     "isdfb_train_fwd_bwd": (C.c_int, [P, P, P, P, P, P, P, P, P, I64, I32, C.POINTER(LossCfg), P, P, P, P, P]),
     "isdfb_zero_grad": (C.c_int, [P, P]),

@@ -23,6 +23,10 @@ int tc_create(isdfb_ctx* ctx);
 void tc_destroy(isdfb_ctx* ctx);
 int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n,
                float* sdf, float* grad, cudaStream_t st);
+int tc_forward_grid(isdfb_ctx* ctx, const float* lin, int dim, const float* scale, const float* transform, float* sdf,
+                    cudaStream_t st);
+int simt_forward_grid(isdfb_ctx* ctx, const float* lin, int dim, const float* scale, const float* transform, float* sdf,
+                      cudaStream_t st);
 int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample,
              const float* dirs_C, const float* T_WC_sample, const float* norm_sample, const float* noise,
              const uint8_t* ray_valid, int64_t n_rays, int32_t S, const isdfb_loss_cfg* loss, float* sdf,
@@ -128,6 +132,7 @@ int isdfb_destroy(isdfb_ctx* ctx) {
   if (ctx->g_own) cudaFree(ctx->g_own);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->adam_dev) cudaFree(ctx->adam_dev);
+  if (ctx->grid_x) cudaFree(ctx->grid_x);
   if (ctx->sample_dev) cudaFree(ctx->sample_dev);
   delete ctx;
   return ISDFB_OK;
@@ -228,6 +233,17 @@ int isdfb_mlp_forward_grad(isdfb_ctx* ctx, const float* x, const float* noise, f
   return tc_forward(ctx, x, noise, noise_std, n, sdf, grad, st);
 }
 
+int isdfb_mlp_forward_grid(isdfb_ctx* ctx, const float* lin, int32_t dim, const float* scale, const float* transform,
+                           float* sdf, void* stream) {
+  ENTER(ctx);
+  if (!ctx->weights_ready) ISDFB_FAIL(ctx, ISDFB_ERR_STATE, "weights not packed (call isdfb_pack_weights)");
+  if (dim <= 0) return ISDFB_OK;
+  if (!lin || !sdf) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_mlp_forward_grid: null argument");
+  if (dim > 2048) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_mlp_forward_grid: dim %d > 2048", dim);
+  if (ctx->cfg.precision == ISDFB_PREC_FP32) return simt_forward_grid(ctx, lin, dim, scale, transform, sdf, st);
+  return tc_forward_grid(ctx, lin, dim, scale, transform, sdf, st);
+}
+
 int isdfb_bounds_pc(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample,
                     const uint8_t* ray_valid, int64_t n_rays, int32_t n_samples, float* bounds, float* grad_vec,
                     void* stream) {
@@ -284,6 +300,10 @@ int isdfb_set_grad_exchange(isdfb_ctx* ctx, float* local0, float* local1, float*
   if (ctx->cfg.precision == ISDFB_PREC_FP32)
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_set_grad_exchange: the fused exchange is implemented by the tensor-core path's "
                                    "gradient flush; fp32 mode uses the caller's all-reduce on isdfb_grad_buffer");
+  if (ctx->lay.E > 256)
+    ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "isdfb_set_grad_exchange: embeddings wider than 256 split the embedding-fed weight blocks "
+                                   "over two weight-gradient jobs that share one gradient tile; the fused per-tile forwarding "
+                                   "assumes one job per tile -- use the all-reduce on isdfb_grad_buffer for this model");
   {   // the library's own buffer becomes the local STAGE of the weight-gradient kernel: start it clean (setup call, may sync)
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e == cudaSuccess) e = cudaMemset(ctx->g_own, 0, ctx->lay.n_packed * sizeof(float));

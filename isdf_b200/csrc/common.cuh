@@ -66,6 +66,7 @@ struct isdfb_ctx {
   // tensor-core path workspace -- see tc_chain.cu
   void* tc;                // opaque
   void* adam_dev;          // device AdamDev {step_size, bc2_sqrt, step} for the graph-safe K6
+  float* grid_x;           // fp32 path: lattice points of one chunk (isdfb_mlp_forward_grid), allocated on first use
   void* sample_dev;        // device FusedSampleState {step, valid, blocks_done} of the fused fast-mode sampler
 };
 

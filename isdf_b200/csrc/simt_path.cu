@@ -468,6 +468,47 @@ int simt_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise
   return ISDFB_OK;
 }
 
+// get_sdf_grid on the CUDA-core path: the lattice points of one chunk are generated into a scratch slab, then K2
+struct GridTr { float v[12]; };
+__global__ void grid_points_kernel_v(const float* __restrict__ lin, int dim, float sx, float sy, float sz, int has_tr,
+                                     GridTr tr, int64_t p0, int64_t n, float* __restrict__ x) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int64_t pg = p0 + q;
+  const int64_t r = pg / dim;
+  const int k = (int)(pg - r * dim), i = (int)(r / dim), j = (int)(r - (int64_t)i * dim);
+  const float gx = __fmul_rn(lin[i], sx), gy = __fmul_rn(lin[j], sy), gz = __fmul_rn(lin[k], sz);
+  float a = gx, b = gy, c = gz;
+  if (has_tr) {
+    const float* t = tr.v;
+    a = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[0], gx), __fmul_rn(t[1], gy)), __fmul_rn(t[2], gz)), t[3]);
+    b = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[4], gx), __fmul_rn(t[5], gy)), __fmul_rn(t[6], gz)), t[7]);
+    c = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t[8], gx), __fmul_rn(t[9], gy)), __fmul_rn(t[10], gz)), t[11]);
+  }
+  x[q * 3] = a; x[q * 3 + 1] = b; x[q * 3 + 2] = c;
+}
+
+int simt_forward_grid(isdfb_ctx* ctx, const float* lin, int dim, const float* scale, const float* transform, float* sdf,
+                      cudaStream_t st) {
+  SimtWs w = carve(ctx);
+  const int64_t n = (int64_t)dim * dim * dim;
+  if (!ctx->grid_x) ISDFB_CUDA_OK(ctx, cudaMalloc(&ctx->grid_x, (size_t)ctx->cap * 3 * sizeof(float)));
+  GridTr tr;
+  memset(&tr, 0, sizeof(tr));
+  if (transform) memcpy(tr.v, transform, sizeof(tr.v));
+  for (int64_t p0 = 0; p0 < n; p0 += ctx->cap) {
+    const int64_t nc = (n - p0 < ctx->cap) ? (n - p0) : ctx->cap;
+    const int64_t np = round_up64(nc, ISDFB_TILE);
+    grid_points_kernel_v<<<nblk(nc, 256), 256, 0, st>>>(lin, dim, scale ? scale[0] : 1.f, scale ? scale[1] : 1.f,
+                                                        scale ? scale[2] : 1.f, transform ? 1 : 0, tr, p0, nc, ctx->grid_x);
+    ISDFB_LAUNCHED(ctx);
+    simt_s1_s2(ctx, w, ctx->grid_x, nullptr, 0.f, nc, np, false, st);
+    ISDFB_CUDA_OK(ctx, cudaMemcpyAsync(sdf + p0, w.sdf, nc * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  ISDFB_CUDA_OK(ctx, cudaGetLastError());
+  return ISDFB_OK;
+}
+
 int simt_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample,
                const float* dirs_C, const float* T_WC_sample, const float* norm_sample,
                const float* noise, const uint8_t* ray_valid, int64_t n_rays, int32_t S,

@@ -85,6 +85,8 @@ struct EpiStepPtrs {                  // per-step pointers (thread offsets inclu
   float* hlast;
   const float* e32;                   // this thread's slice of the fp32 embedding side array (same offsets as aux)
   int ablate, stream;
+  int flags;                          // TcStep::flags (STF_*)
+  int ecol0;                          // EPI_S2_END: first internal embedding column of this step's outputs (256 * eh)
 };
 __device__ __forceinline__ uint32_t sub_a(int c, int h) { return (uint32_t)(8 * c + h) * A_LBO; }
 __device__ __forceinline__ uint32_t sub_d(int c, int h) { return (uint32_t)(8 * c + h) * 256u; }
@@ -151,6 +153,10 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
                                         EpiAcc& acc) {
   const int k0 = 64 * c + T.kcol + 8 * h;
   if (EPI == EPI_RAW) {
+    if (P.flags & STF_RAW_ADD) {       // second embedding half: accumulate onto the parked partial product
+      const float4 pa = ld4(P.part_out + sub_x(c, h)), pb = ld4(P.part_out + sub_x(c, h) + 512);
+      v[0] += pa.x; v[1] += pa.y; v[2] += pa.z; v[3] += pa.w; v[4] += pb.x; v[5] += pb.y; v[6] += pb.z; v[7] += pb.w;
+    }
     if (!(T.ablate & 2)) {
       st4(P.part_out + sub_x(c, h), v[0], v[1], v[2], v[3]);
       st4(P.part_out + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
@@ -204,7 +210,7 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
                          __uint_as_float(o.e1.x), __uint_as_float(o.e1.y), __uint_as_float(o.e1.z), __uint_as_float(o.e1.w)};
 #pragma unroll
     for (int t = 0; t < 8; t += 2) {
-      const int k = k0 + t;
+      const int k = P.ecol0 + k0 + t;
       if (k < two_half) {
         const int pi = k >> 1, d = args.pair_d[pi];
         const float w = (ev[t + 1] * a[t] - ev[t] * a[t + 1]) * (float)(1 << args.pair_f[pi]);
@@ -283,14 +289,18 @@ template <int EPI, int kPasses, int kWide, bool kLean>
 __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T, const EpiStepPtrs& P, ChainSmemTail* tail,
                                          uint32_t d_tmem, uint32_t n, int l, bool train, bool store_state, bool last_step,
                                          float sbar, EpiAcc& acc, int lane) {
-  const bool l_is_cat = (l == args.ic);
+  const bool l_is_cat = P.part_in != nullptr;        // "a parked partial product is added" (concat layer, 2nd embedding half)
+  // A operand left untouched by this epilogue -> the next step's MMA may start at once
+  const bool early_release = (EPI == EPI_RAW && !(P.flags & (STF_PE_E | STF_PE_ABAR))) ||
+                             (EPI == EPI_S2_END && !(P.flags & STF_END_LAST) && !last_step);
+  const bool chunk_release = EPI != EPI_RAW && EPI != EPI_S2_END && !last_step;
   EpiOps oa, ob;
   oa.s = oa.b0 = oa.b1 = oa.e0 = oa.e1 = make_uint4(0, 0, 0, 0);
   ob = oa;
   epi_load<EPI, kPasses, kLean>(P, l_is_cat, T.c0, 0, oa);         // overlaps the tail of this step's MMA
   mbar_wait(smem_u32(&tail->d_full[n & 1]), (n >> 1) & 1);
   tc_fence_after();
-  if (EPI == EPI_RAW) {
+  if (early_release) {
     // A is left untouched: release the next step now (its MMA overlaps this drain of D into a side
     // array).  Arriving only after d_full guarantees every warp finished the previous phase.
     __syncwarp();
@@ -316,7 +326,7 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
       epi_sub<EPI, kPasses, kLean>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
       tmem_ld8(d_tmem + 64 * c + T.kcol + 8, v);
       epi_sub<EPI, kPasses, kLean>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
-      if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
+      if (chunk_release) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
@@ -329,7 +339,7 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
       const int c = (ci + T.c0) & 3;
       float v[8];
       if (T.ablate & 128) {           // DEV: barrier hand-off only (measures the MMA / weight-ring pipeline alone)
-        if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
+        if (chunk_release) {
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
         }
@@ -341,7 +351,7 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
       if (ci < 3) epi_load<EPI, kPasses, kLean>(P, l_is_cat, (c + 1) & 3, 0, oa);
       tmem_ld8(d_tmem + 64 * c + T.kcol + 8, v);
       epi_sub<EPI, kPasses, kLean>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
-      if (EPI != EPI_RAW && EPI != EPI_S2_END && !last_step) {
+      if (chunk_release) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
@@ -409,12 +419,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
               else pf_aux(args.arr_zb2 + l_);
             };
             switch (nx.epi) {
-              case EPI_S1: case EPI_S1_LAST: if (nx.layer == args.ic) pf_aux(args.arr_part + 0); break;
+              case EPI_S1: case EPI_S1_LAST: if (nx.addp >= 0) pf_aux(args.arr_part + nx.addp); break;
               case EPI_S2: pf_sig(nx.layer); break;
-              case EPI_S2_END: pf_aux(args.arr_part + 1); pf_aux(args.arr_e32); break;
+              case EPI_S2_END: pf_aux(args.arr_part + nx.addp); pf_aux(args.arr_e32 + nx.eh); break;
               case EPI_S3: case EPI_S3_LAST:
                 pf_sig(nx.layer); pf_dwl(args.arr_xd + nx.layer);
-                if (nx.layer == args.ic) pf_aux(args.arr_part + 2);
+                if (nx.addp >= 0) pf_aux(args.arr_part + nx.addp);
                 if (nx.epi == EPI_S3_LAST) pf_aux(args.arr_hlast);
                 break;
               case EPI_S4: pf_sig(nx.layer); pf_zb2(nx.layer); break;
@@ -512,44 +522,108 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
       // ---------------- PE stage: x -> e (A operand of the first step) ----------------
       float xs[3] = {0.f, 0.f, 0.f};
       if (real) {
-        const float* xp = args.x + pl * 3;
-        pe_scale_input(args.pe, xp[0], xp[1], xp[2], xs);
-      }
-#pragma unroll 1
-      for (int i = 0; i < 8; ++i) {
-        const int c = i >> 1, h = i & 1;
-        const int k0 = 64 * c + T.kcol + 8 * h;
-        float v[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; jj += 2) {         // internal column order: (sin, cos) pairs, then x y z, then padding
-          const int k = k0 + jj;
-          float va = 0.f, vb = 0.f;
-          if (real) {
-            if (k < two_half) {
-              const int pi = k >> 1;
-              const float xb = pe_project(xs, args.pair_d[pi]) * (float)(1 << args.pair_f[pi]);
-              va = sinf(xb);
-              vb = sinf(__fadd_rn(xb, ISDFB_HALF_PI_F));
-            } else if (k == two_half) {
-              va = xs[0]; vb = xs[1];
-            } else if (k == two_half + 2) {
-              va = xs[2];
-            }
+        float xw0, xw1, xw2;
+        if (args.grid.dim > 0) {             // lattice point (i, j, k) of torch.meshgrid(t, t, t), 'ij' order
+          const int64_t pg = args.p0 + pl;
+          const int d = args.grid.dim;
+          const int64_t r = pg / d;
+          const int k = (int)(pg - r * d), i = (int)(r / d), j = (int)(r - (int64_t)i * d);
+          const float gx = __fmul_rn(args.grid.lin[i], args.grid.scale[0]);
+          const float gy = __fmul_rn(args.grid.lin[j], args.grid.scale[1]);
+          const float gz = __fmul_rn(args.grid.lin[k], args.grid.scale[2]);
+          xw0 = gx; xw1 = gy; xw2 = gz;
+          if (args.grid.has_transform) {     // (R_row * g).sum(-1) + t   (transform.py:291-302)
+            const float* R = args.grid.R;
+            xw0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], gx), __fmul_rn(R[1], gy)), __fmul_rn(R[2], gz)), args.grid.t[0]);
+            xw1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], gx), __fmul_rn(R[4], gy)), __fmul_rn(R[5], gz)), args.grid.t[1]);
+            xw2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], gx), __fmul_rn(R[7], gy)), __fmul_rn(R[8], gz)), args.grid.t[2]);
           }
-          v[jj] = va; v[jj + 1] = vb;
+        } else {
+          const float* xp = args.x + pl * 3;
+          xw0 = xp[0]; xw1 = xp[1]; xw2 = xp[2];
         }
-        put8<kPasses, kLean>(T, v, c, h, true, train ? args.arr_yh : -1);
-        if (store_state && !(args.ablate & 2)) {
-          st4(e32_w + sub_x(c, h), v[0], v[1], v[2], v[3]);
-          st4(e32_w + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
-        }
-        if (h) chunk_ready(c);
+        pe_scale_input(args.pe, xw0, xw1, xw2, xs);
       }
-
       // per-point state carried across steps
       float sdf_reg = 0.f, sbar = 0.f, u3[3] = {0.f, 0.f, 0.f};
+      // embedding half eh (internal columns [256 eh, 256 eh + 256)) -> A image, its dW-layout copy and the fp32 side
+      // array the PE Jacobian / its adjoint read back.  Called at the start of the tile (eh = 0) and, for padded
+      // embeddings wider than 256, from the EPI_RAW step that parks the first half's partial product (STF_PE_E).
+      auto write_e_half = [&](int eh) {
+        float* e32_h = e32_w + (size_t)eh * args.aux_stride;
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const int c = i >> 1, h = i & 1;
+          const int k0 = 256 * eh + 64 * c + T.kcol + 8 * h;
+          float v[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; jj += 2) {         // internal column order: (sin, cos) pairs, then x y z, then padding
+            const int k = k0 + jj;
+            float va = 0.f, vb = 0.f;
+            if (real) {
+              if (k < two_half) {
+                const int pi = k >> 1;
+                const float xb = pe_project(xs, args.pair_d[pi]) * (float)(1 << args.pair_f[pi]);
+                va = sinf(xb);
+                vb = sinf(__fadd_rn(xb, ISDFB_HALF_PI_F));
+              } else if (k == two_half) {
+                va = xs[0]; vb = xs[1];
+              } else if (k == two_half + 2) {
+                va = xs[2];
+              }
+            }
+            v[jj] = va; v[jj + 1] = vb;
+          }
+          put8<kPasses, kLean>(T, v, c, h, true, train ? (eh ? args.arr_yh_e1 : args.arr_yh) : -1);
+          if (store_state && !(args.ablate & 2)) {
+            st4(e32_h + sub_x(c, h), v[0], v[1], v[2], v[3]);
+            st4(e32_h + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
+          }
+          if (h) chunk_ready(c);
+        }
+      };
+      // adjoint of the embedding half eh, abar_e = (u . D_d) 2^f (cos, -sin) | u, -> A image (+ its dW-layout copy)
+      auto write_abar_half = [&](int eh) {
+        const float* e32_h = e32_w + (size_t)eh * args.aux_stride;
+        float4 ea = ld4(e32_h + sub_x(0, 0)), eb = ld4(e32_h + sub_x(0, 0) + 512);
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const int c = i >> 1, h = i & 1;
+          const int k0 = 256 * eh + 64 * c + T.kcol + 8 * h;
+          const float ev[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+          if (i < 7) {                       // own embedding values of the next sub-piece, one ahead
+            const int cn = (i + 1) >> 1, hn = (i + 1) & 1;
+            ea = ld4(e32_h + sub_x(cn, hn));
+            eb = ld4(e32_h + sub_x(cn, hn) + 512);
+          }
+          float v[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; jj += 2) {
+            const int k = k0 + jj;
+            float va = 0.f, vb = 0.f;
+            if (args.ablate & 64) {
+              va = u3[0];
+            } else if (k < two_half) {       // abar_e = (u . D_d) 2^f (cos, -sin)
+              const int pi = k >> 1, d = args.pair_d[pi];
+              const float ud = (u3[0] * c_ico[d][0] + u3[1] * c_ico[d][1] + u3[2] * c_ico[d][2]) * (float)(1 << args.pair_f[pi]);
+              va = ud * ev[jj + 1];
+              vb = -ud * ev[jj];
+            } else if (k == two_half) {
+              va = u3[0]; vb = u3[1];
+            } else if (k == two_half + 2) {
+              va = u3[2];
+            }
+            v[jj] = va; v[jj + 1] = vb;
+          }
+          put8<kPasses, kLean>(T, v, c, h, true, eh ? args.arr_ya_e1 : args.arr_ya);
+          if (h) chunk_ready(c);
+        }
+      };
+      write_e_half(0);
+
       const bool dbg = args.dbg_clock && blockIdx.x == 0 && threadIdx.x == 0 && it == 0;
       if (dbg) args.dbg_clock[0] = clock64();
+      EpiAcc gacc = {0.f, 0.f, 0.f, 0.f};                 // d sdf / d x_s partial sums over this thread's embedding columns
 
       for (int s = 0; s < n_steps; ++s, ++n) {
         const TcStep st = args.steps[s];
@@ -564,15 +638,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         P.dlo = T.dwl_lo + (size_t)(args.arr_xd + l) * T.dwl_stride;
         P.zb2 = T.aux + (size_t)(args.arr_zb2 + l) * T.aux_stride;
         P.zb2h = T.zb2h + (size_t)l * T.sig_stride;
-        P.part_in = T.aux + (size_t)(args.arr_part + (epi == EPI_S2_END ? 1 : ((epi == EPI_S3 || epi == EPI_S3_LAST) ? 2 : 0))) * T.aux_stride;
+        P.part_in = (st.addp >= 0) ? T.aux + (size_t)(args.arr_part + st.addp) * T.aux_stride : nullptr;
         P.part_out = T.aux + (size_t)(args.arr_part + st.aux) * T.aux_stride;
         P.bias = Wp + args.lay_b_off[l];
         P.wout = Wp + args.wout_off;
         P.hlast = T.aux + (size_t)args.arr_hlast * T.aux_stride;
-        P.e32 = e32_w;
+        P.e32 = e32_w + (size_t)st.eh * args.aux_stride;
         P.ablate = args.ablate;
         P.stream = args.stream_loads;
-        EpiAcc acc = {0.f, 0.f, 0.f, 0.f};
+        P.flags = st.flags;
+        P.ecol0 = 256 * st.eh;
+        EpiAcc acc_local = {0.f, 0.f, 0.f, 0.f};
+        if (epi == EPI_S2_END && (st.flags & STF_END_FIRST)) gacc = acc_local;
+        EpiAcc& acc = (epi == EPI_S2_END) ? gacc : acc_local;
         if (dbg) args.dbg_clock[1 + 2 * s] = clock64();
         switch (epi) {
           case EPI_RAW:     epi_step<EPI_RAW, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
@@ -586,7 +664,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         }
 
         if (dbg) args.dbg_clock[2 + 2 * s] = clock64();
-        if (epi == EPI_S1_LAST) {
+        if (epi == EPI_RAW) {
+          // second embedding half of a wide embedding: its A operand replaces the first half's (whose products are done)
+          if (st.flags & STF_PE_E) write_e_half(st.peh);
+          if (st.flags & STF_PE_ABAR) write_abar_half(st.peh);
+        } else if (epi == EPI_S1_LAST) {
           // out layer: combine the four column groups of every point
           red[jg * 128 + p] = acc.raw_acc;
           named_bar_sync(1, EPI_THREADS);
@@ -596,7 +678,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             sdf_reg = raw * c_out;
             if (real) args.sdf_out[pl] = sdf_reg;
           }
-        } else if (epi == EPI_S2_END) {
+        } else if (epi == EPI_S2_END && (st.flags & STF_END_LAST)) {
           red[(0 * 4 + jg) * 128 + p] = acc.gx;
           red[(1 * 4 + jg) * 128 + p] = acc.gy;
           red[(2 * 4 + jg) * 128 + p] = acc.gz;
@@ -646,40 +728,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             named_bar_sync(1, EPI_THREADS);
             const float4 b4 = ld4(bcast + p * 4);
             sbar = b4.x; u3[0] = b4.y; u3[1] = b4.z; u3[2] = b4.w;
-            // abar_e -> A operand of S3 (second pass over this thread's columns)
-            float4 ea = ld4(e32_w + sub_x(0, 0)), eb = ld4(e32_w + sub_x(0, 0) + 512);
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i) {
-              const int c = i >> 1, h = i & 1;
-              const int k0 = 64 * c + T.kcol + 8 * h;
-              const float ev[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
-              if (i < 7) {                       // own embedding values of the next sub-piece, one ahead
-                const int cn = (i + 1) >> 1, hn = (i + 1) & 1;
-                ea = ld4(e32_w + sub_x(cn, hn));
-                eb = ld4(e32_w + sub_x(cn, hn) + 512);
-              }
-              float v[8];
-#pragma unroll
-              for (int jj = 0; jj < 8; jj += 2) {
-                const int k = k0 + jj;
-                float va = 0.f, vb = 0.f;
-                if (args.ablate & 64) {
-                  va = u3[0];
-                } else if (k < two_half) {       // abar_e = (u . D_d) 2^f (cos, -sin)
-                  const int pi = k >> 1, d = args.pair_d[pi];
-                  const float ud = (u3[0] * c_ico[d][0] + u3[1] * c_ico[d][1] + u3[2] * c_ico[d][2]) * (float)(1 << args.pair_f[pi]);
-                  va = ud * ev[jj + 1];
-                  vb = -ud * ev[jj];
-                } else if (k == two_half) {
-                  va = u3[0]; vb = u3[1];
-                } else if (k == two_half + 2) {
-                  va = u3[2];
-                }
-                v[jj] = va; v[jj + 1] = vb;
-              }
-              put8<kPasses, kLean>(T, v, c, h, true, args.arr_ya);
-              if (h) chunk_ready(c);
-            }
+            write_abar_half(0);               // abar_e (first half) -> A operand of S3
           }
         }
       }

@@ -276,5 +276,7 @@ struct TcUnit {
   int64_t w_off;      // offset of the fp32 [256][256] block in the packed parameter buffer
   int32_t ld;         // its leading dimension
   int32_t perm_half;  // > 0: the unit's input axis is the embedding -> internal column order (pe_nat_col)
+  int32_t col0;       // embedding-fed units: first internal embedding column of this unit (0, or 256 for the second
+                      // half when the padded embedding is 512 wide: n_embed_funcs 8 / 10 of the realsense configs)
 };
-#define TC_MAX_UNITS (ISDFB_MAX_HIDDEN_LAYERS + 1)
+#define TC_MAX_UNITS (ISDFB_MAX_HIDDEN_LAYERS + 3)   // layers + concat embedding part + second embedding halves

@@ -141,7 +141,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const TcDwArgs arg
         tmem_ld32(tmem + lane_addr + c * 32, v);
         if (job.perm_half > 0) {     // embedding-fed unit: internal column order -> the reference's (pe_nat_col)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) grad_add(grow + pe_nat_col(c * 32 + i, job.perm_half), v[i], 0);
+          for (int i = 0; i < 32; ++i) {
+            const int nat = pe_nat_col(job.col0 + c * 32 + i, job.perm_half);
+            if (nat < job.ld) grad_add(grow + nat, v[i], 0);      // internal padding columns have no home (and are zero)
+          }
           continue;
         }
 #pragma unroll

@@ -12,12 +12,16 @@ __global__ void tc_pack_kernel(const float* __restrict__ packed, TcUnitTable uni
   const float* W = packed + units.u[unit].w_off;
   const int ld = units.u[unit].ld;
   const int ph = units.u[unit].perm_half;
+  const int col0 = units.u[unit].col0;
   float x[8];
   if (ph > 0) {                     // input axis = embedding: gather the reference columns in internal order
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      x[i] = (orient == 0) ? W[(size_t)n * ld + pe_nat_col(k8 * 8 + i, ph)]      // B[n = out][k = in(internal)]
-                           : W[(size_t)(k8 * 8 + i) * ld + pe_nat_col(n, ph)];   // B[n = in(internal)][k = out]
+    for (int i = 0; i < 8; ++i) {   // internal columns beyond the packed row (pure padding of the 512-wide halves) are zero
+      const int nat = (orient == 0) ? pe_nat_col(col0 + k8 * 8 + i, ph) : pe_nat_col(col0 + n, ph);
+      x[i] = (nat >= ld) ? 0.f
+             : (orient == 0) ? W[(size_t)n * ld + nat]                            // B[n = out][k = in(internal)]
+                             : W[(size_t)(k8 * 8 + i) * ld + nat];                // B[n = in(internal)][k = out]
+    }
   } else if (orient == 0) {         // B[n = out][k = in]
     const float4 a = *reinterpret_cast<const float4*>(W + (size_t)n * ld + k8 * 8);
     const float4 b = *reinterpret_cast<const float4*>(W + (size_t)n * ld + k8 * 8 + 4);

@@ -3,25 +3,63 @@
 #include <new>
 #include <stdlib.h>
 
-static void add_step(TcChainArgs& a, int unit, int orient, int epi, int layer, int aux = 0) {
+static TcStep& add_step(TcChainArgs& a, int unit, int orient, int epi, int layer, int aux = 0) {
   TcStep& s = a.steps[a.n_steps++];
   s.unit = unit; s.orient = orient; s.epi = epi; s.layer = (int16_t)layer; s.aux = (int16_t)aux;
+  s.addp = -1; s.flags = 0; s.peh = 0; s.eh = 0;
+  return s;
 }
 
-static void build_program(const ModelLayout& lay, int mode, TcChainArgs& a) {
-  const int L = lay.L, ic = lay.block + 1, UE = L;   // unit index of the concat layer's embedding part
+// Partial-sum side arrays (indices relative to arr_part).  NE = 1: 0 concat(S1), 1 concat(S2), 2 concat(S3).
+// NE = 2 adds 3: concat(S2) second half, 4: layer-0 first-half partial (S1), 5: the same for S3.
+enum { PART_CAT_S1 = 0, PART_CAT_S2 = 1, PART_CAT_S3 = 2, PART_CAT_S2_H1 = 3, PART_L0_S1 = 4, PART_L0_S3 = 5 };
+
+// Units: 0..L-1 = layer l's main block (layer 0: first embedding half), L = concat embedding part (first half),
+// L+1 = layer 0 second embedding half, L+2 = concat embedding part second half.
+static void build_program(const ModelLayout& lay, int mode, int NE, TcChainArgs& a) {
+  const int L = lay.L, ic = lay.block + 1, UE = L, U0B = L + 1, UEB = L + 2;
   a.n_steps = 0;
-  add_step(a, UE, 0, EPI_RAW, 0, 0);
-  for (int l = 0; l < L; ++l) add_step(a, l, 0, l == L - 1 ? EPI_S1_LAST : EPI_S1, l);
+  // ---- S1: e -> h_0 .. h_{L-1} -> sdf
+  add_step(a, UE, 0, EPI_RAW, 0, PART_CAT_S1);                       // e_0 W_cat,e0^T  (A = e_0, kept)
+  if (NE == 2) {
+    TcStep& r = add_step(a, 0, 0, EPI_RAW, 0, PART_L0_S1);           // e_0 W_0,0^T parked; then e_1 -> A
+    r.flags = STF_PE_E; r.peh = 1;
+    add_step(a, UEB, 0, EPI_RAW, 0, PART_CAT_S1).flags = STF_RAW_ADD;   // += e_1 W_cat,e1^T  (A = e_1, kept)
+  }
+  for (int l = 0; l < L; ++l) {
+    TcStep& t = add_step(a, (l == 0 && NE == 2) ? U0B : l, 0, l == L - 1 ? EPI_S1_LAST : EPI_S1, l);
+    if (l == 0 && NE == 2) t.addp = PART_L0_S1;
+    if (l == ic) t.addp = PART_CAT_S1;
+  }
   if (mode == TC_MODE_FWD) return;
+  // ---- S2: a_{L-1} .. a_e -> d sdf / d x
   for (int l = L - 1; l >= 1; --l) {
-    if (l == ic) add_step(a, UE, 1, EPI_RAW, l, 1);
+    if (l == ic) {
+      add_step(a, UE, 1, EPI_RAW, l, PART_CAT_S2);                   // delta_ic W_cat,e0   (A = delta_ic, kept)
+      if (NE == 2) add_step(a, UEB, 1, EPI_RAW, l, PART_CAT_S2_H1);
+    }
     add_step(a, l, 1, EPI_S2, l - 1);
   }
-  add_step(a, 0, 1, EPI_S2_END, 0);
+  for (int h = 0; h < NE; ++h) {                                     // a_e half h = delta_0 W_0,h + concat part
+    TcStep& t = add_step(a, h == 0 ? 0 : U0B, 1, EPI_S2_END, 0);
+    t.addp = h == 0 ? PART_CAT_S2 : PART_CAT_S2_H1;
+    t.eh = (int16_t)h;
+    t.flags = (h == 0 ? STF_END_FIRST : 0) | (h == NE - 1 ? STF_END_LAST : 0);
+  }
   if (mode == TC_MODE_FWD_GRAD) return;
-  add_step(a, UE, 0, EPI_RAW, 0, 2);
-  for (int l = 0; l < L; ++l) add_step(a, l, 0, l == L - 1 ? EPI_S3_LAST : EPI_S3, l);
+  // ---- S3: abar_e -> dbar_0 .. (forward direction)
+  add_step(a, UE, 0, EPI_RAW, 0, PART_CAT_S3);
+  if (NE == 2) {
+    TcStep& r = add_step(a, 0, 0, EPI_RAW, 0, PART_L0_S3);
+    r.flags = STF_PE_ABAR; r.peh = 1;
+    add_step(a, UEB, 0, EPI_RAW, 0, PART_CAT_S3).flags = STF_RAW_ADD;
+  }
+  for (int l = 0; l < L; ++l) {
+    TcStep& t = add_step(a, (l == 0 && NE == 2) ? U0B : l, 0, l == L - 1 ? EPI_S3_LAST : EPI_S3, l);
+    if (l == 0 && NE == 2) t.addp = PART_L0_S3;
+    if (l == ic) t.addp = PART_CAT_S3;
+  }
+  // ---- S4 (reverse; the two d / d e products are not needed)
   for (int l = L - 1; l >= 1; --l) add_step(a, l, 1, EPI_S4, l - 1);
 }
 
@@ -49,10 +87,11 @@ int tc_dw_init(isdfb_ctx* ctx);
 
 int tc_create(isdfb_ctx* ctx) {
   const ModelLayout& lay = ctx->lay;
-  if (lay.H != TC_H || lay.Ep != TC_H)
+  if (lay.H != TC_H || lay.E > TC_MAX_EH * TC_H)
     ISDFB_FAIL(ctx, ISDFB_ERR_ARG,
-               "tensor-core path supports hidden=256 and embedding <= 256 (n_freqs <= 6); got hidden=%d E=%d. "
+               "tensor-core path supports hidden=256 and embedding <= 512 (n_embed_funcs <= 11); got hidden=%d E=%d. "
                "Use precision fp32 for other shapes.", lay.H, lay.E);
+  const int NE = lay.E > TC_H ? 2 : 1;           // embedding halves of 256 internal columns
   { int rc = tc_chain_init(ctx); if (rc) return rc; rc = tc_dw_init(ctx); if (rc) return rc; }
   TcState* tc = new (std::nothrow) TcState();
   if (!tc) ISDFB_FAIL(ctx, ISDFB_ERR_ARG, "out of host memory");
@@ -63,19 +102,26 @@ int tc_create(isdfb_ctx* ctx) {
   ISDFB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&tc->side, cudaStreamNonBlocking));
   ISDFB_CUDA_OK(ctx, cudaEventCreateWithFlags(&tc->ev_fork, cudaEventDisableTiming));
   ISDFB_CUDA_OK(ctx, cudaEventCreateWithFlags(&tc->ev_join, cudaEventDisableTiming));
-  tc->n_units = L + 1;
+  tc->n_units = L + 1 + (NE == 2 ? 2 : 0);
   const int pe_half = ISDFB_NDIRS * lay.n_freqs;
   for (int l = 0; l < L; ++l) {
     tc->units.u[l].w_off = lay.layer[l].w_off; tc->units.u[l].ld = lay.layer[l].k0;
     tc->units.u[l].perm_half = (l == 0) ? pe_half : 0;
+    tc->units.u[l].col0 = 0;
   }
   tc->units.u[L].w_off = lay.layer[ic].we_off;
   tc->units.u[L].ld = lay.Ep;
   tc->units.u[L].perm_half = pe_half;
+  tc->units.u[L].col0 = 0;
+  if (NE == 2) {                                 // second embedding halves of layer 0 and of the concat layer
+    tc->units.u[L + 1] = tc->units.u[0]; tc->units.u[L + 1].col0 = TC_H;
+    tc->units.u[L + 2] = tc->units.u[L]; tc->units.u[L + 2].col0 = TC_H;
+  }
   const bool lean = ctx->cfg.precision == ISDFB_PREC_BF16X3G;
   tc->tiles_cap = ctx->cap / TC_TILE;
-  tc->n_aux = lean ? 5 : L + 5;              // part x3, e32, h_last (+ zbar2_l as fp32 unless lean)
-  tc->n_dwl = 4 * L + 1;
+  const int n_part = NE == 2 ? 6 : 3;
+  tc->n_aux = n_part + NE + 1 + (lean ? 0 : L);     // partial sums, e32 per half, h_last (+ zbar2_l as fp32 unless lean)
+  tc->n_dwl = 4 * L + 1 + (NE == 2 ? 2 : 0);
   tc->aux_stride = (size_t)tc->tiles_cap * TC_TILE_FLOATS;
   tc->dwl_stride = (size_t)tc->tiles_cap * TC_DWL_TILE_BYTES;
   ISDFB_CUDA_OK(ctx, cudaMalloc(&tc->w_img, (size_t)tc->n_units * 4 * TC_IMG_BYTES));
@@ -93,7 +139,8 @@ int tc_create(isdfb_ctx* ctx) {
   for (int mode = 0; mode < 3; ++mode) {
     TcChainArgs& a = tc->proto[mode];
     memset(&a, 0, sizeof(a));
-    build_program(lay, mode, a);
+    build_program(lay, mode, NE, a);
+    a.n_eh = NE;
     a.mode = mode; a.L = L; a.ic = ic; a.E = lay.E;
     a.prefetch = getenv("ISDFB_NO_PREFETCH") ? 0 : 1;
     a.stagger = getenv("ISDFB_STAGGER") ? atoi(getenv("ISDFB_STAGGER")) : 1;
@@ -111,26 +158,30 @@ int tc_create(isdfb_ctx* ctx) {
     a.aux = tc->aux; a.aux_stride = tc->aux_stride;
     a.dwl_hi = tc->dwl_hi; a.dwl_lo = tc->dwl_lo; a.dwl_stride = tc->dwl_stride;
     a.sig16 = tc->sig16; a.sig16_stride = tc->dwl_stride;
-    a.arr_part = 0; a.arr_e32 = 3; a.arr_hlast = 4; a.arr_zb2 = 5;      // zbar2 (fp32) last: absent in lean mode
+    a.arr_part = 0; a.arr_e32 = n_part; a.arr_hlast = n_part + NE; a.arr_zb2 = n_part + NE + 1;   // zbar2 (fp32): absent in lean mode
     a.lean = lean ? 1 : 0;
     a.zb2h = lean ? tc->sig16 + tc->dwl_stride * L : nullptr;
     if (lean) a.wide = 1;
-    for (int i = 0; i < TC_H / 2; ++i) {      // pair i = (direction, octave) of internal columns 2i, 2i+1
+    for (int i = 0; i < TC_MAX_EH * TC_H / 2; ++i) {      // pair i = (direction, octave) of internal columns 2i, 2i+1
       a.pair_d[i] = (uint8_t)(i < pe_half ? i / lay.n_freqs : 0);
       a.pair_f[i] = (uint8_t)(i < pe_half ? i % lay.n_freqs : 0);
     }
     a.arr_yh = 0; a.arr_ya = L; a.arr_xd = 2 * L; a.arr_xz = 3 * L; a.arr_v = 4 * L;
+    a.arr_yh_e1 = 4 * L + 1; a.arr_ya_e1 = 4 * L + 2;
   }
   // weight-gradient jobs
   TcDwArgs& d = tc->dw;
   memset(&d, 0, sizeof(d));
   const TcChainArgs& a = tc->proto[TC_MODE_TRAIN];
-  for (int u = 0; u <= L; ++u) {
+  for (int u = 0; u < tc->n_units; ++u) {
     for (int half = 0; half < 2; ++half) {
       TcDwJob& j = d.jobs[d.n_jobs++];
       j.half = half;
-      j.ld = TC_H;
-      j.perm_half = (u == 0 || u == L) ? pe_half : 0;
+      j.ld = tc->units.u[u].ld;
+      j.perm_half = tc->units.u[u].perm_half;
+      j.col0 = tc->units.u[u].col0;
+      const bool second = (u > L);                       // second embedding half of layer 0 (L+1) / the concat layer (L+2)
+      const int ya0 = second ? a.arr_ya_e1 : a.arr_ya, yh0 = second ? a.arr_yh_e1 : a.arr_yh;
       if (u < L) {
         j.g_off = lay.layer[u].w_off;
         j.db_off = lay.layer[u].b_off;
@@ -138,11 +189,17 @@ int tc_create(isdfb_ctx* ctx) {
         j.pair[1] = {a.arr_xz + u, a.arr_yh + u, 1};
         j.n_pairs = 2;
         if (u == L - 1) { j.pair[2] = {a.arr_v, -1, 2}; j.n_pairs = 3; }
-      } else {
+      } else if (u == L + 1) {                           // layer 0, second embedding half (bias rides with the first)
+        j.g_off = lay.layer[0].w_off;
+        j.db_off = -1;
+        j.pair[0] = {a.arr_xd + 0, ya0, 0};
+        j.pair[1] = {a.arr_xz + 0, yh0, 0};
+        j.n_pairs = 2;
+      } else {                                           // concat layer, embedding part (half 0 or 1)
         j.g_off = lay.layer[ic].we_off;
         j.db_off = -1;
-        j.pair[0] = {a.arr_xd + ic, a.arr_ya + 0, 0};
-        j.pair[1] = {a.arr_xz + ic, a.arr_yh + 0, 0};
+        j.pair[0] = {a.arr_xd + ic, ya0, 0};
+        j.pair[1] = {a.arr_xz + ic, yh0, 0};
         j.n_pairs = 2;
       }
     }
@@ -176,27 +233,49 @@ static inline int passes_of(const isdfb_ctx* ctx) {
 // the weight-gradient kernel reads single-bf16 operands in lean mode
 static inline int dw_passes_of(const isdfb_ctx* ctx) { return ctx->cfg.precision == ISDFB_PREC_BF16X3 ? 3 : 1; }
 
-int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n, float* sdf,
-               float* grad, cudaStream_t st) {
+static int tc_forward_impl(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n, float* sdf,
+                           float* grad, cudaStream_t st, const TcGrid* grid) {
   TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
   for (int64_t p0 = 0; p0 < n; p0 += ctx->cap) {
     const int64_t nc = (n - p0 < ctx->cap) ? (n - p0) : ctx->cap;
     TcChainArgs a = tc->proto[grad ? TC_MODE_FWD_GRAD : TC_MODE_FWD];
+    if (grid) a.grid = *grid;
     a.n_points = nc;
     a.n_tiles = (int)((nc + TC_TILE - 1) / TC_TILE);
     a.p0 = p0;
-    a.x = x + p0 * 3;
+    a.x = x ? x + p0 * 3 : nullptr;
     a.noise = noise ? noise + p0 : nullptr;
     a.noise_std = noise_std;
     a.sdf_out = sdf + p0;
     a.g_out = grad ? grad + p0 * 3 : nullptr;
-    const int grid = a.n_tiles < tc->num_sms ? a.n_tiles : tc->num_sms;
+    const int n_cta = a.n_tiles < tc->num_sms ? a.n_tiles : tc->num_sms;
     const int pi = prof_begin(tc, st);
-    int rc = tc_chain_launch(ctx, a, passes_of(ctx), grid, st);
+    int rc = tc_chain_launch(ctx, a, passes_of(ctx), n_cta, st);
     if (rc) return rc;
     prof_mark(tc, pi, 1, st);
   }
   return ISDFB_OK;
+}
+
+int tc_forward(isdfb_ctx* ctx, const float* x, const float* noise, float noise_std, int64_t n, float* sdf,
+               float* grad, cudaStream_t st) {
+  return tc_forward_impl(ctx, x, noise, noise_std, n, sdf, grad, st, nullptr);
+}
+
+// K2 over the dim^3 lattice of get_sdf_grid with the query points generated in the kernel (no [dim^3, 3] array in HBM)
+int tc_forward_grid(isdfb_ctx* ctx, const float* lin, int dim, const float* scale, const float* transform, float* sdf,
+                    cudaStream_t st) {
+  TcGrid g;
+  memset(&g, 0, sizeof(g));
+  g.lin = lin; g.dim = dim;
+  for (int i = 0; i < 3; ++i) g.scale[i] = scale ? scale[i] : 1.f;
+  g.has_transform = transform ? 1 : 0;
+  if (transform)
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) g.R[r * 3 + c] = transform[r * 4 + c];
+      g.t[r] = transform[r * 4 + 3];
+    }
+  return tc_forward_impl(ctx, nullptr, nullptr, 0.f, (int64_t)dim * dim * dim, sdf, nullptr, st, &g);
 }
 
 int tc_train(isdfb_ctx* ctx, const float* pc, const float* z_vals, const float* depth_sample, const float* dirs_C,

@@ -15,6 +15,7 @@ struct TcDwJob {
   int32_t ld;
   int64_t db_off;          // packed-gradient offset of the bias (or -1)
   int32_t perm_half;       // > 0: gradient columns are in the internal embedding order (pe_nat_col)
+  int32_t col0;            //      ... starting at this internal column (second embedding half: 256)
 };
 #define TC_MAX_JOBS (2 * TC_MAX_UNITS)
 

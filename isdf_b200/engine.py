@@ -200,6 +200,20 @@ class Engine:
                                             self._stream()))
         return sdf
 
+    def forward_grid(self, lin, scale=None, transform=None):
+        """K2 over the dim^3 lattice x = T (lin_i s_x, lin_j s_y, lin_k s_z), points generated in-kernel (get_sdf_grid)."""
+        lin = _f32(lin, "lin", self.device)
+        dim = lin.numel()
+        sdf = torch.empty(dim, dim, dim, dtype=torch.float32, device=self.device)
+        sc = tr = None
+        if scale is not None:
+            sc = (C.c_float * 3)(*[float(v) for v in torch.as_tensor(scale).reshape(-1).tolist()])
+        if transform is not None:
+            t = torch.as_tensor(transform, dtype=torch.float32).cpu()[:3, :4].reshape(-1).tolist()
+            tr = (C.c_float * 12)(*t)
+        self._ck(self.lib.isdfb_mlp_forward_grid(self._ctx, _ptr(lin), int(dim), sc, tr, _ptr(sdf), self._stream()))
+        return sdf
+
     # ---- N2 ----------------------------------------------------------
     def bounds_pc(self, pc, z_vals, depth_sample, ray_valid=None):
         """loss.bounds_pc (loss.py:56-89): bounds [R,S] and target directions [R,S,3] (row 0 unused)."""

@@ -874,8 +874,13 @@ class Trainer:
         self.scene_scale_np = bounds_extents / ((grid_range[1] - grid_range[0]) * 0.9)
         self.scene_scale = torch.from_numpy(self.scene_scale_np).float().to(self.device)
         self.inv_scene_scale = 1. / self.scene_scale
-        self.grid_pc = transform.make_3D_grid(grid_range, self.grid_dim, self.device, transform=self.bounds_transform,
-                                              scale=self.scene_scale).view(-1, 3).contiguous()
+        # the grid_dim^3 query lattice: kept as its generator (abscissae, scale, box transform) -- get_sdf_grid evaluates
+        # it with the points generated inside the kernel; the [dim^3, 3] array is built only if somebody reads grid_pc
+        self._grid_range = grid_range
+        self._grid_lin = torch.linspace(grid_range[0], grid_range[1], steps=self.grid_dim, device=self.device)
+        self._grid_scale_host = self.scene_scale.cpu()
+        self._grid_tr_host = self.bounds_transform.cpu()
+        self._grid_pc = None
         self.up_ix = int(np.argmax(np.abs(np.matmul(self.up, self.bounds_transform_np[:3, :3]))))
         self.grid_up = self.bounds_transform_np[:3, self.up_ix]
         self.up_aligned = np.dot(self.grid_up, self.up) > 0
@@ -884,11 +889,27 @@ class Trainer:
     def get_sdf_grid(self):
         """SDF on the grid_dim^3 lattice (trainer.py:1426-1444): one K2 call, chunked inside the library
         (the reference loops fc_map.chunks over 100 000-point slices)."""
-        if getattr(self, "grid_pc", None) is None:
-            raise RuntimeError("call set_scene_properties first (grid_pc is not set)")
-        with torch.no_grad():
-            sdf = self.sdf_map(self.grid_pc)
-        return sdf.view(self.grid_dim, self.grid_dim, self.grid_dim)
+        if getattr(self, "_grid_lin", None) is None:
+            if getattr(self, "_grid_pc", None) is None:
+                raise RuntimeError("call set_scene_properties first (grid_pc is not set)")
+            with torch.no_grad():                       # a caller-supplied point set (isdf_window.py:433-434)
+                return self.sdf_map(self._grid_pc).view(self.grid_dim, self.grid_dim, self.grid_dim)
+        return self.sdf_map.engine().forward_grid(self._grid_lin, scale=self._grid_scale_host,
+                                                  transform=self._grid_tr_host)
+
+    @property
+    def grid_pc(self):
+        """[grid_dim^3, 3] query points (trainer.py:139-147), materialised on first read."""
+        if getattr(self, "_grid_pc", None) is None and getattr(self, "_grid_lin", None) is not None:
+            self._grid_pc = transform.make_3D_grid(self._grid_range, self.grid_dim, self.device,
+                                                   transform=self.bounds_transform,
+                                                   scale=self.scene_scale).view(-1, 3).contiguous()
+        return getattr(self, "_grid_pc", None)
+
+    @grid_pc.setter
+    def grid_pc(self, value):
+        self._grid_pc = value
+        self._grid_lin = None                            # an explicit point set replaces the generated lattice
 
     def get_sdf_grid_pc(self, include_gt=False, mask_near_pc=False):
         """[dim,dim,dim,4] numpy array of (x, y, z, sdf) (trainer.py:1446-1481)."""

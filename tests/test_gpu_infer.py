@@ -83,6 +83,30 @@ def test_grid_200_cubed_properties(mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
+def test_grid_lattice_generated_in_kernel_equals_point_array(mode):
+    """isdfb_mlp_forward_grid (get_sdf_grid): the lattice points are generated inside the kernel; same values as K2 over
+    the [dim^3, 3] array geometry.transform.make_3D_grid builds (transform.py:273-304), incl. a ragged last tile."""
+    from isdf.geometry import transform
+    m = _map(75, 1.0, C.rigid_transform(14), mode, max_points=4096)
+    box = C.rigid_transform(3).to(DEV)                       # box -> world
+    scale = torch.tensor([1.7, 0.6, 1.3], device=DEV)
+    for dim in (31, 40):
+        pc = transform.make_3D_grid([-1.0, 1.0], dim, DEV, transform=box, scale=scale).view(-1, 3).contiguous()
+        lin = torch.linspace(-1.0, 1.0, steps=dim, device=DEV)
+        with torch.no_grad():
+            ref = m(pc).view(dim, dim, dim)
+        got = m.engine().forward_grid(lin, scale=scale.cpu(), transform=box.cpu())
+        assert got.shape == (dim, dim, dim)
+        # the kernel rounds R g + t term by term (the reference's (R_row * g).sum(-1) + t), torch.matmul here may fuse /
+        # reorder: coordinates agree to 1 ulp, which the 2^4 octave of the encoding amplifies -> 1e-5 floor in fp32 mode
+        assert P.rel(got.cpu(), ref.cpu()) < max(TOL_RECHUNK[mode], 1e-5)
+    got = m.engine().forward_grid(lin)                        # no scale, no transform
+    pc = transform.make_3D_grid([-1.0, 1.0], 40, DEV).view(-1, 3).contiguous()
+    with torch.no_grad():
+        assert P.rel(got.cpu().view(-1), m(pc).cpu()) < max(TOL_RECHUNK[mode], 1e-5)
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_render_normals_matches_reference(mode):
     from isdf.modules import render
     from isdf.geometry import transform
