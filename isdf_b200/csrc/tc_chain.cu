@@ -678,6 +678,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             sdf_reg = raw * c_out;
             if (real) args.sdf_out[pl] = sdf_reg;
           }
+          // the scratch is written again at S2_END (other warps, >= 3 steps later).  The a_ready / d_full chain already
+          // orders that write after these reads, but compute-sanitizer's racecheck does not model mbarriers: one more
+          // named barrier (~100 cycles per tile) keeps the kernel provably -- and tool-visibly -- hazard free
+          named_bar_sync(1, EPI_THREADS);
         } else if (epi == EPI_S2_END && (st.flags & STF_END_LAST)) {
           red[(0 * 4 + jg) * 128 + p] = acc.gx;
           red[(1 * 4 + jg) * 128 + p] = acc.gy;
@@ -724,6 +728,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
               st4(bcast + p * 4, sb, ux * args.pe.scale, uy * args.pe.scale, uz * args.pe.scale);
             }
           }
+          if (!train) named_bar_sync(1, EPI_THREADS);     // reads of the scratch done before anybody re-uses it (see S1_LAST)
           if (train) {
             named_bar_sync(1, EPI_THREADS);
             const float4 b4 = ld4(bcast + p * 4);
