@@ -392,13 +392,16 @@ def main():
     # a new keyframe layout runs eagerly, the second is captured -- per gradient-buffer parity when data parallel -- and
     # the SM clocks need a few ms of load to settle): at least 30 steps in total, reported in config.warmup_internal
     n_warm = max(args.warmup, 3, 30)
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation, ~100 ms of driver calls) would otherwise
+    # land inside a 20-step (12 ms) timed region; it then samples every 100 ms through warm-up and the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
     for _ in range(n_warm):
         tr.step(sync=False)
     barrier()
     say("warm-up done")
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

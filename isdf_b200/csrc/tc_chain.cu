@@ -146,14 +146,14 @@ __device__ __forceinline__ int rot_kstep(int ks, int rot) {
   return ((((ks >> 2) + (rot >> 2)) & 3) << 2) | (((ks & 3) + rot) & 3);
 }
 
-template <int EPI, int kPasses, bool kLean>
+template <int EPI, int kPasses, bool kLean, int kNE>
 __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, const EpiStepPtrs& P, const EpiOps& o,
                                         float* v /* 8 accumulator columns of this sub-piece */, int c, int h, int l,
                                         bool l_is_cat, bool train, bool store_state, bool last_step, float sbar,
                                         EpiAcc& acc) {
   const int k0 = 64 * c + T.kcol + 8 * h;
   if (EPI == EPI_RAW) {
-    if (P.flags & STF_RAW_ADD) {       // second embedding half: accumulate onto the parked partial product
+    if (kNE == 2 && (P.flags & STF_RAW_ADD)) {       // second embedding half: accumulate onto the parked partial product
       const float4 pa = ld4(P.part_out + sub_x(c, h)), pb = ld4(P.part_out + sub_x(c, h) + 512);
       v[0] += pa.x; v[1] += pa.y; v[2] += pa.z; v[3] += pa.w; v[4] += pb.x; v[5] += pb.y; v[6] += pb.z; v[7] += pb.w;
     }
@@ -210,7 +210,7 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
                          __uint_as_float(o.e1.x), __uint_as_float(o.e1.y), __uint_as_float(o.e1.z), __uint_as_float(o.e1.w)};
 #pragma unroll
     for (int t = 0; t < 8; t += 2) {
-      const int k = P.ecol0 + k0 + t;
+      const int k = (kNE == 2 ? P.ecol0 : 0) + k0 + t;
       if (k < two_half) {
         const int pi = k >> 1, d = args.pair_d[pi];
         const float w = (ev[t + 1] * a[t] - ev[t] * a[t + 1]) * (float)(1 << args.pair_f[pi]);
@@ -285,14 +285,14 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
 }
 
 // one whole step of the epilogue for this thread (8 sub-pieces), operands fetched one sub-piece ahead
-template <int EPI, int kPasses, int kWide, bool kLean>
+template <int EPI, int kPasses, int kWide, bool kLean, int kNE>
 __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T, const EpiStepPtrs& P, ChainSmemTail* tail,
                                          uint32_t d_tmem, uint32_t n, int l, bool train, bool store_state, bool last_step,
                                          float sbar, EpiAcc& acc, int lane) {
   const bool l_is_cat = P.part_in != nullptr;        // "a parked partial product is added" (concat layer, 2nd embedding half)
   // A operand left untouched by this epilogue -> the next step's MMA may start at once
-  const bool early_release = (EPI == EPI_RAW && !(P.flags & (STF_PE_E | STF_PE_ABAR))) ||
-                             (EPI == EPI_S2_END && !(P.flags & STF_END_LAST) && !last_step);
+  const bool early_release = (EPI == EPI_RAW && (kNE == 1 || !(P.flags & (STF_PE_E | STF_PE_ABAR)))) ||
+                             (EPI == EPI_S2_END && kNE == 2 && !(P.flags & STF_END_LAST) && !last_step);
   const bool chunk_release = EPI != EPI_RAW && EPI != EPI_S2_END && !last_step;
   EpiOps oa, ob;
   oa.s = oa.b0 = oa.b1 = oa.e0 = oa.e1 = make_uint4(0, 0, 0, 0);
@@ -323,9 +323,9 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
       }
       float v[8];
       tmem_ld8(d_tmem + 64 * c + T.kcol, v);
-      epi_sub<EPI, kPasses, kLean>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      epi_sub<EPI, kPasses, kLean, kNE>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
       tmem_ld8(d_tmem + 64 * c + T.kcol + 8, v);
-      epi_sub<EPI, kPasses, kLean>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      epi_sub<EPI, kPasses, kLean, kNE>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
       if (chunk_release) {
         fence_proxy_async_smem();
         __syncwarp();
@@ -347,10 +347,10 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
       }
       epi_load<EPI, kPasses, kLean>(P, l_is_cat, c, 1, ob);
       tmem_ld8(d_tmem + 64 * c + T.kcol, v);
-      epi_sub<EPI, kPasses, kLean>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      epi_sub<EPI, kPasses, kLean, kNE>(args, T, P, oa, v, c, 0, l, l_is_cat, train, store_state, last_step, sbar, acc);
       if (ci < 3) epi_load<EPI, kPasses, kLean>(P, l_is_cat, (c + 1) & 3, 0, oa);
       tmem_ld8(d_tmem + 64 * c + T.kcol + 8, v);
-      epi_sub<EPI, kPasses, kLean>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
+      epi_sub<EPI, kPasses, kLean, kNE>(args, T, P, ob, v, c, 1, l, l_is_cat, train, store_state, last_step, sbar, acc);
       if (chunk_release) {
         fence_proxy_async_smem();
         __syncwarp();
@@ -361,7 +361,10 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
   tc_fence_before();
 }
 
-template <int kPasses, int kWide, bool kLean>
+// kNE = embedding halves of 256 internal columns the program was built for (1: E <= 256 -- every shipped default
+// config; 2: E <= 512).  A template parameter so that the single-half kernel carries none of the second half's
+// run-time flag tests (they cost 2.6 % of the default workload's kernel time when they were run-time only).
+template <int kPasses, int kWide, bool kLean, int kNE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_constant__ TcChainArgs args) {
   using Cfg = ChainCfg<kPasses>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -643,28 +646,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         P.bias = Wp + args.lay_b_off[l];
         P.wout = Wp + args.wout_off;
         P.hlast = T.aux + (size_t)args.arr_hlast * T.aux_stride;
-        P.e32 = e32_w + (size_t)st.eh * args.aux_stride;
+        P.e32 = (kNE == 2) ? e32_w + (size_t)st.eh * args.aux_stride : e32_w;
         P.ablate = args.ablate;
         P.stream = args.stream_loads;
         P.flags = st.flags;
         P.ecol0 = 256 * st.eh;
         EpiAcc acc_local = {0.f, 0.f, 0.f, 0.f};
-        if (epi == EPI_S2_END && (st.flags & STF_END_FIRST)) gacc = acc_local;
+        if (epi == EPI_S2_END && (kNE == 1 || (st.flags & STF_END_FIRST))) gacc = acc_local;
         EpiAcc& acc = (epi == EPI_S2_END) ? gacc : acc_local;
         if (dbg) args.dbg_clock[1 + 2 * s] = clock64();
         switch (epi) {
-          case EPI_RAW:     epi_step<EPI_RAW, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S1:      epi_step<EPI_S1, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S1_LAST: epi_step<EPI_S1_LAST, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S2:      epi_step<EPI_S2, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S2_END:  epi_step<EPI_S2_END, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S3:      epi_step<EPI_S3, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          case EPI_S3_LAST: epi_step<EPI_S3_LAST, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
-          default:          epi_step<EPI_S4, kPasses, kWide, kLean>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_RAW:     epi_step<EPI_RAW, kPasses, kWide, kLean, kNE>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S1:      epi_step<EPI_S1, kPasses, kWide, kLean, kNE>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S1_LAST: epi_step<EPI_S1_LAST, kPasses, kWide, kLean, kNE>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S2:      epi_step<EPI_S2, kPasses, kWide, kLean, kNE>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S2_END:  epi_step<EPI_S2_END, kPasses, kWide, kLean, kNE>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S3:      epi_step<EPI_S3, kPasses, kWide, kLean, kNE>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          case EPI_S3_LAST: epi_step<EPI_S3_LAST, kPasses, kWide, kLean, kNE>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
+          default:          epi_step<EPI_S4, kPasses, kWide, kLean, kNE>(args, T, P, tail, d_tmem, n, l, train, store_state, last_step, sbar, acc, lane); break;
         }
 
         if (dbg) args.dbg_clock[2 + 2 * s] = clock64();
-        if (epi == EPI_RAW) {
+        if (kNE == 2 && epi == EPI_RAW) {
           // second embedding half of a wide embedding: its A operand replaces the first half's (whose products are done)
           if (st.flags & STF_PE_E) write_e_half(st.peh);
           if (st.flags & STF_PE_ABAR) write_abar_half(st.peh);
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
           // orders that write after these reads, but compute-sanitizer's racecheck does not model mbarriers: one more
           // named barrier (~100 cycles per tile) keeps the kernel provably -- and tool-visibly -- hazard free
           named_bar_sync(1, EPI_THREADS);
-        } else if (epi == EPI_S2_END && (st.flags & STF_END_LAST)) {
+        } else if (epi == EPI_S2_END && (kNE == 1 || (st.flags & STF_END_LAST))) {
           red[(0 * 4 + jg) * 128 + p] = acc.gx;
           red[(1 * 4 + jg) * 128 + p] = acc.gy;
           red[(2 * 4 + jg) * 128 + p] = acc.gz;
@@ -763,25 +766,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
   if (warp == EPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
+template <int kPasses, int kWide, bool kLean, int kNE>
+static void chain_launch_t(const TcChainArgs& args, int grid, cudaStream_t st) {
+  tc_chain_kernel<kPasses, kWide, kLean, kNE><<<grid, NUM_THREADS, ChainCfg<kPasses>::kSmem, st>>>(args);
+}
+
 int tc_chain_launch(isdfb_ctx* ctx, const TcChainArgs& args, int passes, int grid, cudaStream_t st) {
+  const bool two = args.n_eh == 2;       // wide embeddings: always the 16-column-TMEM-load epilogue variant
   if (passes == 3) {
-    if (args.lean) tc_chain_kernel<3, 1, true><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
-    else if (args.wide) tc_chain_kernel<3, 1, false><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
-    else tc_chain_kernel<3, 0, false><<<grid, NUM_THREADS, ChainCfg<3>::kSmem, st>>>(args);
+    if (args.lean) { if (two) chain_launch_t<3, 1, true, 2>(args, grid, st); else chain_launch_t<3, 1, true, 1>(args, grid, st); }
+    else if (two) chain_launch_t<3, 1, false, 2>(args, grid, st);
+    else if (args.wide) chain_launch_t<3, 1, false, 1>(args, grid, st);
+    else chain_launch_t<3, 0, false, 1>(args, grid, st);
   } else {
-    if (args.wide) tc_chain_kernel<1, 1, false><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
-    else tc_chain_kernel<1, 0, false><<<grid, NUM_THREADS, ChainCfg<1>::kSmem, st>>>(args);
+    if (two) chain_launch_t<1, 1, false, 2>(args, grid, st);
+    else if (args.wide) chain_launch_t<1, 1, false, 1>(args, grid, st);
+    else chain_launch_t<1, 0, false, 1>(args, grid, st);
   }
   ISDFB_LAUNCHED(ctx);
   ISDFB_CUDA_OK(ctx, cudaGetLastError());
   return ISDFB_OK;
 }
 
+template <int kPasses, int kWide, bool kLean, int kNE>
+static cudaError_t chain_attr_t() {
+  return cudaFuncSetAttribute(tc_chain_kernel<kPasses, kWide, kLean, kNE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              ChainCfg<kPasses>::kSmem);
+}
+
 int tc_chain_init(isdfb_ctx* ctx) {
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<3>::kSmem));
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
-  ISDFB_CUDA_OK(ctx, cudaFuncSetAttribute(tc_chain_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<1>::kSmem));
+  ISDFB_CUDA_OK(ctx, (chain_attr_t<3, 0, false, 1>()));
+  ISDFB_CUDA_OK(ctx, (chain_attr_t<3, 1, false, 1>()));
+  ISDFB_CUDA_OK(ctx, (chain_attr_t<3, 1, false, 2>()));
+  ISDFB_CUDA_OK(ctx, (chain_attr_t<3, 1, true, 1>()));
+  ISDFB_CUDA_OK(ctx, (chain_attr_t<3, 1, true, 2>()));
+  ISDFB_CUDA_OK(ctx, (chain_attr_t<1, 0, false, 1>()));
+  ISDFB_CUDA_OK(ctx, (chain_attr_t<1, 1, false, 1>()));
+  ISDFB_CUDA_OK(ctx, (chain_attr_t<1, 1, false, 2>()));
   return ISDFB_OK;
 }
