@@ -14,6 +14,7 @@ Put this repo's root on sys.path BEFORE the reference checkout and the reference
 import importlib.util
 import os
 import sys
+import warnings
 
 import isdf_b200
 from isdf_b200 import modules, geometry, datasets, eval  # noqa: F401,A004
@@ -45,9 +46,16 @@ def _fallback_getattr(mod, ref_file):
             spec.loader.exec_module(ref)
             state["ref"] = ref
         try:
-            return getattr(state["ref"], name)
+            val = getattr(state["ref"], name)
         except AttributeError:
             raise AttributeError("module %r has no attribute %r (nor has the reference's %s)" % (mod.__name__, name, ref_file))
+        if name not in state.setdefault("warned", set()):
+            # never silent: a name of a mirrored (hot-path) module that is served by the reference's Python code is worth
+            # knowing about -- it is either out-of-scope tooling (to_trimesh, plotting helpers) or a gap in this package
+            state["warned"].add(name)
+            warnings.warn("isdf_b200: %s.%s is not provided by the B200 implementation; using the reference's %s"
+                          % (mod.__name__, name, ref_file), stacklevel=2)
+        return val
     return __getattr__
 
 
