@@ -21,6 +21,14 @@
 #include "tc_chain.cuh"
 #include "pe_loss.cuh"
 
+// Timing ablations (ISDFB_ABLATE, tools/ablate*.sh) are a DEV build option: compiled in only with -DISDFB_DEV_ABLATE.
+// In the product build every test below is a compile-time false -- they were 5 predicate tests (LOP3 + ISETP + BRA)
+// per 8-element sub-piece of every epilogue, ~10 % of the issued instructions.
+#ifdef ISDFB_DEV_ABLATE
+#define ABL(flags, bit) ((flags) & (bit))
+#else
+#define ABL(flags, bit) 0
+#endif
 #define EPI_WARPS 16
 #define EPI_THREADS (EPI_WARPS * 32)
 #define NUM_THREADS (EPI_THREADS + 128)   // + one helper warpgroup: MMA issuer, weight producer, two idle warps
@@ -98,11 +106,11 @@ template <int kPasses, bool kLean>
 __device__ __forceinline__ void put8(const EpiT& T, const float* x, int c, int h, bool to_a, int dwl_arr) {
   uint4 hi, lo;
   if (kPasses == 3 && (to_a || !kLean)) split8(x, hi, lo); else hi = pack8_hi(x);
-  if (to_a && !(T.ablate & 32)) {
+  if (to_a && !ABL(T.ablate, 32)) {
     *reinterpret_cast<uint4*>(T.a_hi + sub_a(c, h)) = hi;
     if (kPasses == 3) *reinterpret_cast<uint4*>(T.a_lo + sub_a(c, h)) = lo;
   }
-  if (dwl_arr >= 0 && !(T.ablate & 1)) {
+  if (dwl_arr >= 0 && !ABL(T.ablate, 1)) {
     const size_t off = (size_t)dwl_arr * T.dwl_stride + sub_d(c, h);
     *reinterpret_cast<uint4*>(T.dwl_hi + off) = hi;
     if (kPasses == 3 && !kLean) *reinterpret_cast<uint4*>(T.dwl_lo + off) = lo;
@@ -111,8 +119,8 @@ __device__ __forceinline__ void put8(const EpiT& T, const float* x, int c, int h
 
 template <int EPI, int kPasses, bool kLean>
 __device__ __forceinline__ void epi_load(const EpiStepPtrs& P, bool l_is_cat, int c, int h, EpiOps& o) {
-  if (P.ablate & 8) return;
-  auto ld = [&](const void* q) -> uint4 { return P.stream ? ld_stream(q) : *reinterpret_cast<const uint4*>(q); };
+  if (ABL(P.ablate, 8)) return;
+  auto ld = [&](const void* q) -> uint4 { return ld_stream(q); };   // read-once side state: never allocates in L1
   if (EPI == EPI_S2 || EPI == EPI_S3 || EPI == EPI_S3_LAST || EPI == EPI_S4)
     o.s = ld(P.sigp + sub_a(c, h));
   if (EPI == EPI_S3 || EPI == EPI_S3_LAST) {
@@ -157,7 +165,7 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
       const float4 pa = ld4(P.part_out + sub_x(c, h)), pb = ld4(P.part_out + sub_x(c, h) + 512);
       v[0] += pa.x; v[1] += pa.y; v[2] += pa.z; v[3] += pa.w; v[4] += pb.x; v[5] += pb.y; v[6] += pb.z; v[7] += pb.w;
     }
-    if (!(T.ablate & 2)) {
+    if (!ABL(T.ablate, 2)) {
       st4(P.part_out + sub_x(c, h), v[0], v[1], v[2], v[3]);
       st4(P.part_out + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
     }
@@ -169,20 +177,20 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
       z[4] += __uint_as_float(o.b1.x); z[5] += __uint_as_float(o.b1.y); z[6] += __uint_as_float(o.b1.z); z[7] += __uint_as_float(o.b1.w);
     }
     float hh[8], sg[8];
-    if (T.ablate & 16) {
+    if (ABL(T.ablate, 16)) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) { hh[t] = fmaxf(z[t], 0.f); sg[t] = z[t] > 0.f ? 1.f : 0.f; }
     } else {
 #pragma unroll
       for (int t = 0; t < 8; ++t) softplus100_fast(z[t], hh[t], sg[t]);
     }
-    if (store_state && !(T.ablate & 4)) *reinterpret_cast<uint4*>(P.sigw + sub_a(c, h)) = pack_unorm16x8(sg);
+    if (store_state && !ABL(T.ablate, 4)) *reinterpret_cast<uint4*>(P.sigw + sub_a(c, h)) = pack_unorm16x8(sg);
     if (EPI == EPI_S1) {
       put8<kPasses, kLean>(T, hh, c, h, true, (train && l + 1 < args.L) ? args.arr_yh + l + 1 : -1);
     } else {
       const float4 wa = ld4(P.wout + k0), wb = ld4(P.wout + k0 + 4);
       const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-      if (train && !(T.ablate & 2)) {
+      if (train && !ABL(T.ablate, 2)) {
         st4(P.hlast + sub_x(c, h), hh[0], hh[1], hh[2], hh[3]);
         st4(P.hlast + sub_x(c, h) + 512, hh[4], hh[5], hh[6], hh[7]);
       }
@@ -200,7 +208,7 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
     for (int t = 0; t < 8; ++t) v[t] *= sg[t];
     put8<kPasses, kLean>(T, v, c, h, true, train ? args.arr_xd + l : -1);
   } else if (EPI == EPI_S2_END) {
-    if (T.ablate & 64) { acc.gx += v[0]; return; }
+    if (ABL(T.ablate, 64)) { acc.gx += v[0]; return; }
     // PE Jacobian in the internal column order (tc_common.cuh): columns (2i, 2i+1) = (sin, cos) of pair i, so
     // d e / d xb = (cos, -sin) is thread-local:  g_xs += D_d 2^f (cos a_sin - sin a_cos);  x y z follow the pairs
     const int two_half = 2 * ISDFB_NDIRS * args.pe.n_freqs;
@@ -244,7 +252,7 @@ __device__ __forceinline__ void epi_sub(const TcChainArgs& args, const EpiT& T, 
       v[t] = v[t] * sg[t];                 // abar = dbar * sigma
     }
     if (EPI == EPI_S3) {
-      if (!(T.ablate & 2)) {
+      if (!ABL(T.ablate, 2)) {
         if (kLean) {
           *reinterpret_cast<uint4*>(P.zb2h + sub_a(c, h)) = pack8_hi(zb);
         } else {
@@ -338,7 +346,7 @@ __device__ __forceinline__ void epi_step(const TcChainArgs& args, const EpiT& T,
     for (int ci = 0; ci < 4; ++ci) {
       const int c = (ci + T.c0) & 3;
       float v[8];
-      if (T.ablate & 128) {           // DEV: barrier hand-off only (measures the MMA / weight-ring pipeline alone)
+      if (ABL(T.ablate, 128)) {           // DEV: barrier hand-off only (measures the MMA / weight-ring pipeline alone)
         if (chunk_release) {
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tail->a_ready[c]));
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             mbar_wait(smem_u32(&tail->w_empty[stage]), ph ^ 1);
             const uint32_t bar = smem_u32(&tail->w_full[stage]);
             const uint32_t dst = smem_u32(w_ring + stage * Cfg::kStageBytes);
-            if (args.ablate & 512) { mbar_arrive(bar); continue; }      // DEV: no weight traffic at all
+            if (ABL(args.ablate, 512)) { mbar_arrive(bar); continue; }      // DEV: no weight traffic at all
             const int kse = rot_kstep(ks, rot);
             mbar_arrive_expect_tx(bar, Cfg::kStageBytes);
             bulk_g2s(dst, img_hi + (size_t)kse * KSTEP_IMG_BYTES, KSTEP_IMG_BYTES, bar);
@@ -468,8 +476,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             const uint32_t b_base = smem_u32(w_ring + stage * Cfg::kStageBytes);
             const uint64_t ah = umma_desc(smem_u32(a_hi) + kse * 2 * A_LBO, A_LBO, 128);
             const uint64_t bh = umma_desc(b_base, B_LBO, 128);
-            if (!(args.ablate & 256)) tc_mma_f16(d_tmem, ah, bh, idesc, ks != 0);
-            if (kPasses == 3 && !(args.ablate & 256)) {
+            if (!ABL(args.ablate, 256)) tc_mma_f16(d_tmem, ah, bh, idesc, ks != 0);
+            if (kPasses == 3 && !ABL(args.ablate, 256)) {
               const uint64_t al = umma_desc(smem_u32(a_lo) + kse * 2 * A_LBO, A_LBO, 128);
               const uint64_t bl = umma_desc(b_base + KSTEP_IMG_BYTES, B_LBO, 128);
               tc_mma_f16(d_tmem, al, bh, idesc, 1);
@@ -578,7 +586,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             v[jj] = va; v[jj + 1] = vb;
           }
           put8<kPasses, kLean>(T, v, c, h, true, train ? (eh ? args.arr_yh_e1 : args.arr_yh) : -1);
-          if (store_state && !(args.ablate & 2)) {
+          if (store_state && !ABL(args.ablate, 2)) {
             st4(e32_h + sub_x(c, h), v[0], v[1], v[2], v[3]);
             st4(e32_h + sub_x(c, h) + 512, v[4], v[5], v[6], v[7]);
           }
@@ -604,7 +612,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
           for (int jj = 0; jj < 8; jj += 2) {
             const int k = k0 + jj;
             float va = 0.f, vb = 0.f;
-            if (args.ablate & 64) {
+            if (ABL(args.ablate, 64)) {
               va = u3[0];
             } else if (k < two_half) {       // abar_e = (u . D_d) 2^f (cos, -sin)
               const int pi = k >> 1, d = args.pair_d[pi];
