@@ -189,3 +189,46 @@ def test_alias_package_layers_over_the_reference_checkout():
     assert "visualisation from /root/reference/isdf/visualisation/__init__.py" in out
     assert "accuracy_comp (fallback): isdf_reference.eval.metrics" in out
     assert "isdf.eval.plot_utils from /root/reference/isdf/eval/plot_utils.py" in out
+
+
+def test_reference_copy_is_verbatim_and_steps_on_cpu(tmp_path):
+    """oracle/make_ref.py + oracle/ref_step.py: the CPU arm of bench.py.  The copy under oracle/_ref must be byte-identical
+    to the read-only checkout (SHA-256 manifest), import through the shim without this repo's `isdf` alias getting in the way,
+    and its UNMODIFIED Trainer must step on device 'cpu' when driven like train.py does."""
+    import hashlib
+    import json
+    import subprocess
+    import sys
+    from oracle import make_ref, ref_shim
+    if not os.path.isdir("/root/reference/isdf/modules"):
+        if not ref_shim.available():
+            pytest.skip("neither /root/reference nor oracle/_ref is present")
+    else:
+        assert make_ref.populate()
+        man = json.load(open(os.path.join(make_ref.DST, "MANIFEST.json")))
+        assert len(man["files"]) >= 30 and "isdf/modules/trainer.py" in man["files"]
+        for rel, digest in man["files"].items():
+            for root in (make_ref.SRC, make_ref.DST):
+                assert hashlib.sha256(open(os.path.join(root, rel), "rb").read()).hexdigest() == digest, (root, rel)
+    # a tiny config through the same stepper bench.py uses, in a fresh interpreter (the shim evicts `isdf*` modules)
+    code = (
+        "import sys, json; sys.path.insert(0, %r)\n"
+        "import torch; torch.set_num_threads(4)\n"
+        "import bench\n"
+        "from oracle import ref_step\n"
+        "wl = dict(bench.WORKLOADS['default']); wl.update(H=120, W=160, fx=100.0, fy=100.0, cx=79.5, cy=59.5, n_rays=16)\n"
+        "st = ref_step.RefTrainerStepper(bench.make_config(wl, 'fp32', 'reference'), n_keyframes=6)\n"
+        "a = st.step(); b = st.step()\n"
+        "print(json.dumps({'file': st.trainer_file, 'pts': st.points_per_step, 'loss': [a[0], b[0]]}))\n"
+        % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert "isdf_b200" not in out["file"] and out["file"].endswith("isdf/modules/trainer.py")
+    assert out["pts"] == 16 * 5 * 27 and all(0.0 < v < 10.0 for v in out["loss"])
+
+
+def test_bench_cpu_thread_count_is_one_per_physical_core():
+    import bench
+    n = bench.host_threads()
+    assert 1 <= n <= (os.cpu_count() or 1) and torch.get_num_threads() == n
