@@ -1,6 +1,15 @@
 // C-ABI entry points (include/isdf_b200.h): argument checks, context lifetime, precision dispatch.
 #include "common.cuh"
 #include <new>
+#include <nvtx3/nvToolsExt.h>    // header-only NVTX v3: ranges cost nothing unless a profiler (nsys / ncu --nvtx) is attached
+
+// one NVTX range per C-ABI entry (= per kernel family: K1 sampling, K2/K3 forward, K4 fused step, K5, K6, N2, N3, A0):
+// `ncu --nvtx --nvtx-include "isdfb_train_fwd_bwd/"` or an nsys timeline groups the launches by the reference block
+// they replace
+struct NvtxScope {
+  explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+  ~NvtxScope() { nvtxRangePop(); }
+};
 
 char g_isdfb_create_err[512] = "";
 
@@ -145,6 +154,7 @@ int64_t isdfb_launch_count(const isdfb_ctx* ctx) { return ctx ? ctx->launches : 
 
 #define ENTER(ctx)                                                     \
   if (!(ctx)) return ISDFB_ERR_ARG;                                    \
+  NvtxScope _nvtx(__func__);                                           \
   ISDFB_CUDA_OK(ctx, cudaSetDevice((ctx)->device));                    \
   cudaStream_t st = (cudaStream_t)stream;
 

@@ -48,6 +48,16 @@ class SyntheticStream:
         image = np.full((self.H, self.W, 3), 128, dtype=np.uint8)
         item = {"image": image, "depth": self.depth(k), "T": self.pose(k)}
         if self.cache_frames:
+            # cached frames stand in for decoded camera images waiting in a capture queue: kept in page-locked memory, so
+            # Trainer.get_data can copy them to the device without a staging pass ("depth_pinned" aliases "depth")
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    pin = torch.from_numpy(item["depth"]).pin_memory()
+                    item["depth_pinned"] = pin
+                    item["depth"] = pin.numpy()
+            except Exception:      # noqa: BLE001 -- pinning is an optimisation only
+                pass
             self._cache[k] = item
         return item
 
