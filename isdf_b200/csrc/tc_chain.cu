@@ -451,9 +451,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
             const uint32_t dst = smem_u32(w_ring + stage * Cfg::kStageBytes);
             if (ABL(args.ablate, 512)) { mbar_arrive(bar); continue; }      // DEV: no weight traffic at all
             const int kse = rot_kstep(ks, rot);
-            mbar_arrive_expect_tx(bar, Cfg::kStageBytes);
+            const bool blo = kPasses == 3 && !(st.flags & STF_NO_BLO);
+            mbar_arrive_expect_tx(bar, blo ? Cfg::kStageBytes : KSTEP_IMG_BYTES);
             bulk_g2s(dst, img_hi + (size_t)kse * KSTEP_IMG_BYTES, KSTEP_IMG_BYTES, bar);
-            if (kPasses == 3) bulk_g2s(dst + KSTEP_IMG_BYTES, img_lo + (size_t)kse * KSTEP_IMG_BYTES, KSTEP_IMG_BYTES, bar);
+            if (blo) bulk_g2s(dst + KSTEP_IMG_BYTES, img_lo + (size_t)kse * KSTEP_IMG_BYTES, KSTEP_IMG_BYTES, bar);
           }
         }
       }
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
     for (int it = 0; it < my_tiles; ++it) {
       for (int s = 0; s < n_steps; ++s, ++n) {
         const uint32_t d_tmem = tmem + (n & 1) * 256;
+        const bool blo = !(args.steps[s].flags & STF_NO_BLO);
         for (int ks = 0; ks < N_KSTEPS; ++ks, ++j) {
           const int kse = rot_kstep(ks, rot);
           if ((ks & 3) == 0) mbar_wait(smem_u32(&tail->a_ready[kse >> 2]), n & 1);
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
               const uint64_t al = umma_desc(smem_u32(a_lo) + kse * 2 * A_LBO, A_LBO, 128);
               const uint64_t bl = umma_desc(b_base + KSTEP_IMG_BYTES, B_LBO, 128);
               tc_mma_f16(d_tmem, al, bh, idesc, 1);
-              tc_mma_f16(d_tmem, ah, bl, idesc, 1);
+              if (blo) tc_mma_f16(d_tmem, ah, bl, idesc, 1);
             }
             tc_commit(smem_u32(&tail->w_empty[stage]));
             if (ks == N_KSTEPS - 1) tc_commit(smem_u32(&tail->d_full[n & 1]));

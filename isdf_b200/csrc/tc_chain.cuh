@@ -14,7 +14,9 @@ enum {
   STF_PE_E = 2,        // EPI_RAW: after the drain write the embedding half `peh` into A (S1)
   STF_PE_ABAR = 4,     // EPI_RAW: after the drain write the adjoint abar_e half `peh` into A (S3)
   STF_END_FIRST = 8,   // EPI_S2_END: first embedding half -> reset the d sdf/dx accumulators
-  STF_END_LAST = 16    // EPI_S2_END: last embedding half -> reduce, loss, then abar_e half 0 into A
+  STF_END_LAST = 16,   // EPI_S2_END: last embedding half -> reduce, loss, then abar_e half 0 into A
+  STF_NO_BLO = 32      // experiment (ISDFB_GRAD_2PASS): skip the A_hi * B_lo pass of this product (gradient-only sweeps S3 / S4):
+                       // the weights enter as single bf16, only their hi image is streamed
 };
 struct TcStep {
   int32_t unit;     // weight unit (tc_pack.cu)

@@ -61,6 +61,12 @@ static void build_program(const ModelLayout& lay, int mode, int NE, TcChainArgs&
   }
   // ---- S4 (reverse; the two d / d e products are not needed)
   for (int l = L - 1; l >= 1; --l) add_step(a, l, 1, EPI_S4, l - 1);
+  if (getenv("ISDFB_GRAD_2PASS"))          // experiment: weights as single bf16 in the gradient-only sweeps
+    for (int s = 0; s < a.n_steps; ++s)
+      if (a.steps[s].epi == EPI_S3 || a.steps[s].epi == EPI_S3_LAST || a.steps[s].epi == EPI_S4 ||
+          (a.steps[s].epi == EPI_RAW && a.steps[s].aux != PART_CAT_S1 && a.steps[s].aux != PART_CAT_S2 &&
+           a.steps[s].aux != PART_CAT_S2_H1 && a.steps[s].aux != PART_L0_S1))
+        a.steps[s].flags |= STF_NO_BLO;
 }
 
 void tc_destroy(isdfb_ctx* ctx) {
