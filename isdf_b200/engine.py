@@ -166,9 +166,13 @@ class Engine:
         return dict(pc=pc, z_vals=z, indices_b=ib, indices_h=ih, indices_w=iw, dirs_C_sample=dirs_C, depth_sample=d_s,
                     T_WC_sample=T_s, norm_sample=n_s, ray_valid=valid, noise=noise, inv_count_dev=inv)
 
-    def ingest_normals(self, depth, cam):
+    def ingest_normals(self, depth, cam, out=None):
         depth = _f32(depth, "depth", self.device)
-        out = torch.empty(*depth.shape, 3, dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty(*depth.shape, 3, dtype=torch.float32, device=self.device)
+        elif (out.shape != (*depth.shape, 3) or out.dtype != torch.float32 or out.device != self.device
+              or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous float32 [%s, 3] tensor on %s" % (tuple(depth.shape), self.device))
         self._ck(self.lib.isdfb_ingest_normals(self._ctx, _ptr(depth), C.byref(cam), _ptr(out), self._stream()))
         return out
 

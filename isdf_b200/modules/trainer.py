@@ -147,6 +147,7 @@ class Trainer:
         self._plist = None
         self._loss_host = None
         self._stage = None
+        self._dev_stage = None
         self.dist_world, self.dist_rank = parallel.world()
         # data-parallel gradient exchange: "multicast" = fused into the K4 flush over NVLink multicast,
         # "nccl" = one ncclAllReduce, "auto" = multicast when every rank can set it up
@@ -384,12 +385,25 @@ class Trainer:
                 np.copyto(self._stage[1].numpy(), T_np, casting="same_kind")
                 pinned = s.get("depth_pinned")
                 if pinned is not None and pinned.is_pinned():
-                    # the source already decoded the frame into page-locked memory: no staging copy
-                    depth = pinned.view(1, self.H, self.W).to(self.device, non_blocking=True)
+                    src = pinned.view(1, self.H, self.W)    # the source decoded the frame into page-locked memory already
                 else:
                     np.copyto(self._stage[0].numpy(), depth_np, casting="same_kind")
-                    depth = self._stage[0].to(self.device, non_blocking=True)
-                T = self._stage[1].to(self.device, non_blocking=True)
+                    src = self._stage[0]
+                if len(idxs) == 1:
+                    # single-frame ingest (the drivers' pattern, train.py:117-123): the device side is a persistent staging
+                    # set, so a steady-state ingest allocates nothing (with 8 ranks ingesting in the same step, concurrent
+                    # cudaMalloc calls stalled single ranks for ~20 ms).  The returned FrameData aliases it until add_data /
+                    # add_frame copies it into the keyframe buffer -- consume it before the next get_data.
+                    if self._dev_stage is None:
+                        self._dev_stage = (torch.empty(1, self.H, self.W, dtype=torch.float32, device=self.device),
+                                           torch.empty(1, 4, 4, dtype=torch.float32, device=self.device),
+                                           torch.empty(1, self.H, self.W, 3, dtype=torch.float32, device=self.device))
+                    depth, T = self._dev_stage[0], self._dev_stage[1]
+                    depth.copy_(src, non_blocking=True)
+                    T.copy_(self._stage[1], non_blocking=True)
+                else:
+                    depth = src.to(self.device, non_blocking=True)
+                    T = self._stage[1].to(self.device, non_blocking=True)
                 self._stage_evt.record()
                 im = None
             else:
@@ -400,7 +414,8 @@ class Trainer:
                              depth_batch_np=depth_np, T_WC_batch=T, T_WC_batch_np=T_np)
             if self.do_normal:
                 if fast:
-                    data.normal_batch = self.sdf_map.engine().ingest_normals(depth[0], self.cam)[None, :]
+                    nout = self._dev_stage[2][0] if (len(idxs) == 1 and self._dev_stage is not None) else None
+                    data.normal_batch = self.sdf_map.engine().ingest_normals(depth[0], self.cam, out=nout)[None, :]
                 else:
                     pc = transform.pointcloud_from_depth_torch(depth[0], self.fx, self.fy, self.cx, self.cy)
                     data.normal_batch = transform.estimate_pointcloud_normals(pc)[None, :]
@@ -409,6 +424,13 @@ class Trainer:
 
     def add_data(self, data, replace=False):
         replace = self.last_is_keyframe is False      # a non-keyframe is overwritten by the next frame
+        if (len(self.frames) == 0 and self._dev_stage is not None and data.depth_batch is not None
+                and data.depth_batch.data_ptr() == self._dev_stage[0].data_ptr()):
+            # the very first frame is ADOPTED by the buffer (no copy, data_util.py:52-60): it must not alias the staging set
+            data.depth_batch = data.depth_batch.clone()
+            data.T_WC_batch = data.T_WC_batch.clone()
+            if data.normal_batch is not None:
+                data.normal_batch = data.normal_batch.clone()
         self.frames.add_frame_data(data, replace)
         if self.last_is_keyframe:
             print("New keyframe. KF ids:", self.frames.frame_id[:-1])
