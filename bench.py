@@ -441,10 +441,10 @@ def main():
         for _ in range(2):
             losses, _ = tr.step()
             _ = float(losses["total_loss"])
+    import gc
+    gc.collect()              # BEFORE the barrier: a collection takes 10-20 ms and differs per rank
     barrier()
     step_ms, ingest_ms = [], []
-    import gc
-    gc.collect()
     if not os.environ.get("ISDFB_BENCH_KEEP_GC"):
         gc.disable()          # a generation-2 collection (10-20 ms with torch + numpy loaded) inside a 13 ms timed region
                               # would be reported as +1 ms per step; collections resume right after the region
