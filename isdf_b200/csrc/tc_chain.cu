@@ -92,7 +92,7 @@ struct EpiStepPtrs {                  // per-step pointers (thread offsets inclu
   const float *bias, *wout;
   float* hlast;
   const float* e32;                   // this thread's slice of the fp32 embedding side array (same offsets as aux)
-  int ablate, stream;
+  int ablate;
   int flags;                          // TcStep::flags (STF_*)
   int ecol0;                          // EPI_S2_END: first internal embedding column of this step's outputs (256 * eh)
 };
@@ -658,7 +658,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_chain_kernel(const __grid_c
         P.hlast = T.aux + (size_t)args.arr_hlast * T.aux_stride;
         P.e32 = (kNE == 2) ? e32_w + (size_t)st.eh * args.aux_stride : e32_w;
         P.ablate = args.ablate;
-        P.stream = args.stream_loads;
         P.flags = st.flags;
         P.ecol0 = 256 * st.eh;
         EpiAcc acc_local = {0.f, 0.f, 0.f, 0.f};

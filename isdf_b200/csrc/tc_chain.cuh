@@ -49,9 +49,8 @@ struct TcChainArgs {
   int32_t tile0;             // ... starting at this tile of the chunk
   int32_t prefetch;          // 1: bulk-prefetch the next step's side arrays into L2 (producer warp)
   int32_t stagger;           // 1: per-CTA rotation of the K order (rot_kstep) against L2 hot-spotting on the weights
-  int32_t stream_loads;      // 1: side-state loads bypass L1 allocation (ld.global.L1::no_allocate)
   int32_t wide;              // 1: epilogue variant with 16-column TMEM loads (two interleaved chains per chunk)
-  int32_t ablate;            // DEV ONLY (env ISDFB_ABLATE, results invalid): 1 no dW-layout stores, 2 no aux stores,
+  int32_t ablate;            // DEV ONLY (env ISDFB_ABLATE + a build with -DISDFB_DEV_ABLATE; results invalid): 1 no dW-layout stores, 2 no aux stores,
                              // 4 no sigma stores, 8 no side loads, 16 relu instead of softplus, 32 no A-image stores,
                              // 64 no PE-Jacobian / abar_e math -- timing ablations for profiles/
   int64_t n_points;          // real points in this chunk

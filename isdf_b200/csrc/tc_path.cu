@@ -150,7 +150,6 @@ int tc_create(isdfb_ctx* ctx) {
     a.mode = mode; a.L = L; a.ic = ic; a.E = lay.E;
     a.prefetch = getenv("ISDFB_NO_PREFETCH") ? 0 : 1;
     a.stagger = getenv("ISDFB_STAGGER") ? atoi(getenv("ISDFB_STAGGER")) : 1;
-    a.stream_loads = getenv("ISDFB_STREAM_LOADS") ? atoi(getenv("ISDFB_STREAM_LOADS")) : 1;
     a.wide = getenv("ISDFB_EPI_WIDE") ? atoi(getenv("ISDFB_EPI_WIDE")) : 1;
     a.ablate = getenv("ISDFB_ABLATE") ? atoi(getenv("ISDFB_ABLATE")) : 0;
     a.dbg_clock = tc->dbg_clock;
