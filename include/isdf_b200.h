@@ -272,6 +272,15 @@ int isdfb_zero_grad_buffer(isdfb_ctx* ctx, int32_t which, void* stream);
 int isdfb_profile_enable(isdfb_ctx* ctx, int32_t enable);
 int isdfb_profile_read(isdfb_ctx* ctx, double* chain_ms, double* dw_ms, int64_t* n_chain, int64_t* n_dw);
 
+/* Host-only: the step program the fused kernel runs for a model shape (no CUDA call).  mode 0 forward, 1 forward +
+ * d sdf/dx, 2 training.  steps_out receives 8 int32 per step: weight unit, orientation (0: X W^T, 1: X W), epilogue kind
+ * (0 RAW, 1 S1, 2 S1_LAST, 3 S2, 4 S2_END, 5 S3, 6 S3_LAST, 7 S4), hidden layer, partial-sum array written, partial-sum
+ * array added (-1 none), flags (1 accumulate, 2 then-write-e, 4 then-write-abar_e, 8 first / 16 last embedding half),
+ * (generated half << 8 | output half).  Returns the step count; < 0: bad argument (-1), shape not taken by the tcgen05
+ * path (-2), buffer too small (-4).  The sweeps are SURVEY.md 8a's S1..S4 (fc_map.py:94-111, 12-22; trainer.py:981). */
+int isdfb_debug_program(int32_t n_freqs, int32_t hidden, int32_t block, int32_t mode, int32_t* steps_out,
+                        int32_t max_steps);
+
 /* ---- debug hook (tests only): raw per-tile side state of the tensor-core path -------------
  * aux: fp32 arrays [n_aux][tiles_cap][256*128] in the aux layout, dwl_hi/lo: bf16 arrays
  * [n_dwl][tiles_cap][64 KB] in the dW layout, sig16: unorm16 sigma [L][tiles_cap][64 KB]

@@ -72,6 +72,7 @@ SIGNATURES = {
     "isdfb_grad_buffer": (C.c_int, [P, C.POINTER(P), C.POINTER(I64)]),
     "isdfb_profile_enable": (C.c_int, [P, I32]),
     "isdfb_profile_read": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(I64)]),
+    "isdfb_debug_program": (C.c_int, [I32, I32, I32, I32, C.POINTER(I32), I32]),
     "isdfb_debug_buffers": (C.c_int, [P, C.POINTER(P), C.POINTER(I64), C.POINTER(P), C.POINTER(P), C.POINTER(I64),
                                       C.POINTER(I32), C.POINTER(I32), C.POINTER(I64), C.POINTER(P)]),
 }

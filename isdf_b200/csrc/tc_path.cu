@@ -69,6 +69,36 @@ static void build_program(const ModelLayout& lay, int mode, int NE, TcChainArgs&
         a.steps[s].flags |= STF_NO_BLO;
 }
 
+// Host-only view of the step program (no CUDA call, no context): what the chain kernel will run for a model shape.
+// Each step is written as 8 int32: unit, orient, epi, layer, aux, addp, flags, (peh << 8 | eh).  Returns the number of
+// steps, or a negative error.  Used by tests/test_abi.py to pin the programs (CPU suite) and by tools.
+extern "C" int isdfb_debug_program(int32_t n_freqs, int32_t hidden, int32_t block, int32_t mode, int32_t* steps_out,
+                                   int32_t max_steps) {
+  if (!steps_out || n_freqs < 1 || block < 1 || 2 * block + 2 > ISDFB_MAX_HIDDEN_LAYERS || mode < 0 || mode > 2) return -1;
+  ModelLayout lay;
+  memset(&lay, 0, sizeof(lay));
+  lay.n_freqs = n_freqs;
+  lay.E = 2 * ISDFB_NDIRS * n_freqs + 3;
+  lay.H = hidden;
+  lay.block = block;
+  lay.L = 2 * block + 2;
+  if (lay.H != TC_H || lay.E > TC_MAX_EH * TC_H) return -2;          // shapes the tcgen05 path refuses
+  TcChainArgs* a = new (std::nothrow) TcChainArgs();
+  if (!a) return -3;
+  memset(a, 0, sizeof(*a));
+  build_program(lay, mode, lay.E > TC_H ? 2 : 1, *a);
+  const int n = a->n_steps;
+  if (n > max_steps || n > TC_MAX_STEPS) { delete a; return -4; }
+  for (int i = 0; i < n; ++i) {
+    const TcStep& t = a->steps[i];
+    int32_t* o = steps_out + 8 * i;
+    o[0] = t.unit; o[1] = t.orient; o[2] = t.epi; o[3] = t.layer; o[4] = t.aux; o[5] = t.addp; o[6] = t.flags;
+    o[7] = (t.peh << 8) | t.eh;
+  }
+  delete a;
+  return n;
+}
+
 void tc_destroy(isdfb_ctx* ctx) {
   TcState* tc = reinterpret_cast<TcState*>(ctx->tc);
   if (!tc) return;
