@@ -232,3 +232,17 @@ def test_bench_cpu_thread_count_is_one_per_physical_core():
     import bench
     n = bench.host_threads()
     assert 1 <= n <= (os.cpu_count() or 1) and torch.get_num_threads() == n
+
+
+def test_bench_cpu_arm_falls_back_to_the_port_without_the_reference(monkeypatch):
+    """bench.make_cpu_stepper: with neither /root/reference nor oracle/_ref the CPU arm times the committed restatement
+    (kind 'port') instead of failing; with the reference it reports kind 'reference'."""
+    import bench
+    from oracle import ref_shim
+    wl = dict(bench.WORKLOADS["default"])
+    wl.update(H=64, W=96, fx=60.0, fy=60.0, cx=47.5, cy=31.5, n_rays=8)
+    monkeypatch.setattr(ref_shim, "available", lambda: False)
+    st, kind, what = bench.make_cpu_stepper(wl, 5, None)
+    assert kind == "port" and "cpu_step" in what
+    dt, pts, per = bench.time_cpu(st, 0, 1)
+    assert pts == 8 * 5 * 27 and dt > 0 and len(per) == 1
