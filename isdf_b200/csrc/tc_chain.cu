@@ -6,7 +6,7 @@
 // and writes the A operand of step s+1 in place.  Weights stream from L2 through a ring of bulk
 // (TMA) copies of pre-packed operand images, one UMMA K-step (16) per stage.
 //
-// Warp roles (576 threads):
+// Warp roles (640 threads):
 //   warps 0-15  epilogue: warp w owns TMEM lane quadrant w%4 (points 32(w%4)..+31) and 16 of the 64
 //               columns of every K chunk of the next step's A operand; 4 warps per scheduler hide the
 //               ALU/SFU/LSU latency of the element-wise math; chunk 0 of the next A operand is done
@@ -18,6 +18,11 @@
 //
 // Precision: kPasses = 3 -> every product is A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with bf16 hi/lo splits
 // and fp32 accumulation (~fp32 accuracy); kPasses = 1 -> single bf16 pass (fast mode).
+// kLean (precision "bf16x3g", the default): the per-point side state handed to the weight-gradient kernel, the S3
+// read-back of delta_l and zbar2_l are single bf16 -- half the HBM traffic, sdf / d sdf/dx / losses unchanged.
+// kNE = embedding halves of 256 internal columns (2: E = 381 / 465 of the realsense / franka configs): every
+// embedding-fed product is then two products whose partial results are parked (EPI_RAW) and added (TcStep::addp).
+// The step program itself is built on the host (tc_path.cu build_program; pinned by tests/test_abi.py).
 #include "tc_chain.cuh"
 #include "pe_loss.cuh"
 
