@@ -185,3 +185,31 @@ def test_graph_replays_keep_the_adamw_step_count(seq, tmp_path):
     tr.optimiser.step()
     for a, b in zip(ref_params, tr.sdf_map.parameters()):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
+def test_configs_with_gt_sdf_dir_take_the_scene_box_from_the_config(seq):
+    """replicaCAD.json / scannet.json set dataset.gt_sdf_dir: the reference feeds the oriented scene box of the GT mesh into
+    the positional encoding (trainer.py:78-81, 121-129, 421-426).  Here the box comes from b200.scene_box (trimesh is not a
+    dependency); without it the constructor must refuse rather than train a different model."""
+    from isdf.modules import trainer
+    cfg = json.load(open(seq))
+    cfg["dataset"]["gt_sdf_dir"] = "/nonexistent/gt_sdfs/apt_2/"
+    with pytest.raises(NotImplementedError, match="b200.scene_box"):
+        trainer.Trainer("cuda:0", cfg, precision=MODES[0])
+    T = C.rigid_transform(21)
+    cfg["b200"] = {"scene_box": {"T_extent_to_scene": T.tolist(), "bounds_extents": [6.0, 3.0, 5.0]}}
+    tr = trainer.Trainer("cuda:0", cfg, precision=MODES[0], grid_dim=16)
+    assert tr.gt_scene and torch.allclose(tr.inv_bounds_transform.cpu(), T)
+    assert tr.sdf_map.positional_encoding.transform is tr.inv_bounds_transform      # the PE input transform
+    tr.last_is_keyframe = True
+    tr.add_data(tr.get_data([0]))
+    losses, _ = tr.step()
+    assert torch.isfinite(torch.tensor(float(losses["total_loss"])))
+    x = torch.rand(64, 3, device="cuda:0")
+    a = tr.sdf_map(x)
+    tr2 = trainer.Trainer("cuda:0", {k: v for k, v in cfg.items() if k != "b200"} | {"dataset": {k: v for k, v in cfg["dataset"].items()
+                                                                                             if k != "gt_sdf_dir"}},
+                          precision=MODES[0])
+    tr2.sdf_map.load_state_dict(tr.sdf_map.state_dict())
+    assert not torch.allclose(tr2.sdf_map(x), a, atol=1e-4)       # same weights, no box -> a different function of x
+    assert tr.get_sdf_grid().shape == (16, 16, 16)
